@@ -1,0 +1,121 @@
+/*
+ * meshanything_b200.h -- C ABI of libmeshanything_b200.so (sm_100a).
+ *
+ * The reference (buaacyw/MeshAnything) exposes no FFI: its boundary is the Python surface
+ * (SURVEY.md section 8b).  These entry points are the seams inside `MeshAnything.forward`
+ * (/root/reference/MeshAnything/models/meshanything.py:134-176) that the drop-in Python facade
+ * (MeshAnything/models/meshanything.py in this repo) binds with ctypes; INTEGRATION.md shows the
+ * binding.  Plain pointers and sizes only; all pointers are DEVICE pointers unless noted; the
+ * caller (PyTorch) owns every allocation; no entry point allocates device memory or synchronises
+ * the device unless stated.  Every function returns 0 on success, non-zero on error
+ * (ma_last_error() gives the message).  `stream` is a cudaStream_t passed as void*.
+ *
+ * Numerics: fp16 weights/activations at the reference's autocast rounding points, fp32
+ * accumulation in the canonical order of DESIGN.md section 3 (bit-exact against oracle/).
+ */
+#ifndef MESHANYTHING_B200_H
+#define MESHANYTHING_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MA_ABI_VERSION 1
+#define MA_MAX_LAYERS 32
+
+/* epilogues of ma_linear_f16 */
+#define MA_EPI_NONE 0
+#define MA_EPI_RELU 1 /* OPTDecoderLayer activation_fn (opt-350m: relu) */
+#define MA_EPI_GELU 2 /* nn.GELU() exact erf: transformer_blocks.py:239, BERT intermediate */
+
+int ma_abi_version(void);
+const char* ma_last_error(void);
+
+/* ---- canonical building blocks (also the unit-test surface) ------------------------------- */
+
+/* y[m][n] = fp16( dot(W[n][:], x[m][:]) + bias[n] ) then epilogue.  Replaces nn.Linear under fp16
+ * autocast (every q/k/v/out_proj/fc1/fc2/lm_head/input_layer call of shape_opt.py:243,155 and HF
+ * OPTDecoderLayer).  W [N][K] fp16 row-major, bias [N] fp16 or NULL, x [M][ldx] fp16, y [M][ldy]
+ * fp16.  K % 256 == 0. */
+int ma_linear_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
+                  int epilogue, void* stream);
+
+/* h = x (+ float(res16)); out = LayerNorm(h) * gamma + beta  (fp32 statistics).  Replaces the
+ * residual add + nn.LayerNorm pairs of OPTDecoderLayer (post-LN) and the miche/BERT LayerNorms.
+ * x fp32 [M][W] or NULL (then h = float(res16)), res16 fp16 [M][W] or NULL; out32 / out16 optional.
+ * W in {768, 1024}. */
+int ma_layernorm(const float* x, const void* res16, const float* gamma, const float* beta, float eps, int M, int W,
+                 float* out32, void* out16, void* stream);
+
+/* Row m attends keys [0, nkeys[m]) of cache slot slots[m] (NULL: slot 0): softmax(q k^T * scale) v,
+ * fp32 accumulate, fp16 out.  Replaces flash_attn_func (OptFlashAttention2) and the eager einsum
+ * attention of transformer_blocks.py:57-74,166-185.
+ * q [M][ldq] fp16 (head h at columns h*64..); K,V: [slot][head][T][64] fp16; out [M][ldo] fp16;
+ * scratch: ma_attention_scratch_bytes(M, H, max_keys) bytes, zero-initialised once by the caller. */
+size_t ma_attention_scratch_bytes(int M, int H, int max_keys);
+int ma_attention_f16(const void* q, int ldq, const void* K, const void* V, long T, int H, const int* slots,
+                     const int* nkeys, int max_keys, int M, float scale, void* out, int ldo, void* scratch,
+                     void* stream);
+
+/* ---- ShapeOPT decoder (shape_opt.py:188-460 + HF generate) --------------------------------- */
+
+typedef struct {
+  int n_layers, vocab, codebook, npos;
+  const void* wqkv[MA_MAX_LAYERS]; /* fp16 [3072][1024]: q_proj, k_proj, v_proj rows stacked */
+  const void* bqkv[MA_MAX_LAYERS]; /* fp16 [3072] */
+  const void* wo[MA_MAX_LAYERS];   /* fp16 [1024][1024] out_proj */
+  const void* bo[MA_MAX_LAYERS];
+  const void* w1[MA_MAX_LAYERS];   /* fp16 [4096][1024] fc1 */
+  const void* b1[MA_MAX_LAYERS];
+  const void* w2[MA_MAX_LAYERS];   /* fp16 [1024][4096] fc2 */
+  const void* b2[MA_MAX_LAYERS];
+  const float* ln1g[MA_MAX_LAYERS]; /* self_attn_layer_norm */
+  const float* ln1b[MA_MAX_LAYERS];
+  const float* ln2g[MA_MAX_LAYERS]; /* final_layer_norm (per layer) */
+  const float* ln2b[MA_MAX_LAYERS];
+  const void* lm_head;    /* fp16 [vocab][1024], no bias (shape_opt.py:22) */
+  const void* tok_table;  /* fp16 [codebook][1024] = input_layer(quantize_codebooks[0]) (shape_opt.py:243),
+                             folded once at load time with ma_linear_f16 */
+  const float* extra;     /* fp32 [3][1024]    extra_embeds */
+  const float* tok_pos;   /* fp32 [12][1024]   token_embed_positions */
+  const float* cond;      /* fp32 [2][1024]    cond_embed */
+  const float* pos;       /* fp32 [npos][1024] embed_positions incl. the 2 offset rows */
+} ma_decoder_weights;
+
+typedef struct {
+  int do_sample;   /* 0: greedy argmax on fp16 logits, lowest index on ties */
+  int top_k;       /* 50 in the reference (meshanything.py:156) */
+  float top_p;     /* 0.95 (meshanything.py:157) */
+  uint64_t seed;
+} ma_sampling;
+
+size_t ma_kv_cache_bytes(int n_layers, int B, int tmax);
+size_t ma_decoder_workspace_bytes(int B, int tmax);
+
+/* transformer.generate(inputs_embeds=prefix, max_new_tokens=..., bos/eos/pad) of
+ * meshanything.py:144-162.  prefix fp32 [B][257][1024]; out_ids int32 [B][max_new] (rows that
+ * finished are padded with pad_id, HF semantics); out_lens int32 [B] = tokens generated up to and
+ * including eos.  kv: ma_kv_cache_bytes, ws: ma_decoder_workspace_bytes (contents undefined on
+ * entry).  Optional test hooks: forced_ids int32 [B][max_new] (teacher forcing: fed instead of the
+ * pick), logits_out fp16 [max_new][B][vocab].  Enqueues everything on `stream`; polls a pinned flag
+ * for early exit but never blocks on the device. */
+int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, int tmax, int max_new,
+                       const ma_sampling* sampling, int eos_id, int pad_id, void* kv, void* ws, int32_t* out_ids,
+                       int32_t* out_lens, const int32_t* forced_ids, void* logits_out, int flags, void* stream);
+
+/* flags of ma_decode_generate */
+#define MA_GEN_NO_GRAPH 1   /* plain launches instead of a CUDA graph per step */
+#define MA_GEN_NO_FAST 2    /* batch-1: use the general batched kernels instead of the fused GEMV path */
+#define MA_GEN_NO_PDL 4     /* batch-1 fast path without programmatic dependent launch */
+#define MA_GEN_NO_EARLY_EXIT 8
+
+/* number of kernels launched by the library since load (bench.py's gpu_launches) */
+unsigned long long ma_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,139 @@
+"""ctypes binding of libmeshanything_b200.so (include/meshanything_b200.h).
+
+The library is built in-tree by `meshanything_b200.build` (nvcc, sm_100a).  There is no CPU or
+PyTorch fallback: if the shared object cannot be loaded every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+MA_MAX_LAYERS = 32
+EPI_NONE, EPI_RELU, EPI_GELU = 0, 1, 2
+GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT = 1, 2, 4, 8
+
+_vp = C.c_void_p
+
+
+class DecoderWeights(C.Structure):
+    _fields_ = (
+        [("n_layers", C.c_int), ("vocab", C.c_int), ("codebook", C.c_int), ("npos", C.c_int)]
+        + [(n, _vp * MA_MAX_LAYERS) for n in ("wqkv", "bqkv", "wo", "bo", "w1", "b1", "w2", "b2",
+                                              "ln1g", "ln1b", "ln2g", "ln2b")]
+        + [(n, _vp) for n in ("lm_head", "tok_table", "extra", "tok_pos", "cond", "pos")]
+    )
+
+
+class Sampling(C.Structure):
+    _fields_ = [("do_sample", C.c_int), ("top_k", C.c_int), ("top_p", C.c_float), ("seed", C.c_uint64)]
+
+
+_lib = None
+
+EXPORTS = [
+    "ma_abi_version", "ma_last_error", "ma_launch_count", "ma_linear_f16", "ma_layernorm",
+    "ma_attention_scratch_bytes", "ma_attention_f16", "ma_kv_cache_bytes", "ma_decoder_workspace_bytes",
+    "ma_decode_generate",
+]
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def lib():
+    """Load (building if stale and nvcc is available) the shared library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path) or (os.environ.get("MA_B200_REBUILD") == "1"):
+        path = _build.build()
+    L = C.CDLL(path)
+    L.ma_abi_version.restype = C.c_int
+    L.ma_last_error.restype = C.c_char_p
+    L.ma_launch_count.restype = C.c_ulonglong
+    L.ma_linear_f16.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
+    L.ma_layernorm.argtypes = [_vp, _vp, _vp, _vp, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp]
+    L.ma_attention_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ma_attention_scratch_bytes.restype = C.c_size_t
+    L.ma_attention_f16.argtypes = [_vp, C.c_int, _vp, _vp, C.c_long, C.c_int, _vp, _vp, C.c_int, C.c_int,
+                                   C.c_float, _vp, C.c_int, _vp, _vp]
+    L.ma_kv_cache_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.ma_kv_cache_bytes.restype = C.c_size_t
+    L.ma_decoder_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    L.ma_decoder_workspace_bytes.restype = C.c_size_t
+    L.ma_decode_generate.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.POINTER(Sampling),
+                                     C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]
+    if L.ma_abi_version() != 1:
+        raise RuntimeError("libmeshanything_b200.so: ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().ma_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("meshanything_b200: tensors must live on a CUDA device (no CPU fallback)")
+
+
+# ---------------------------------------------------------------- canonical building blocks
+
+def linear_f16(w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor, epilogue: int = EPI_NONE,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp16(x @ w.T + bias) with the canonical accumulation order.  w [N,K] fp16, x [M,K] fp16."""
+    _need_cuda(w, bias, x)
+    assert w.dtype == torch.float16 and x.dtype == torch.float16 and w.is_contiguous()
+    assert x.dim() == 2 and x.stride(1) == 1
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    check(lib().ma_linear_f16(ptr(w), ptr(bias), ptr(x), x.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
+                              stream_ptr()), "ma_linear_f16")
+    return out
+
+
+def layernorm(x: Optional[torch.Tensor], res16: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+              eps: float = 1e-5, want32: bool = True, want16: bool = True):
+    _need_cuda(x, res16, gamma, beta)
+    src = x if x is not None else res16
+    M, W = src.shape
+    o32 = torch.empty((M, W), dtype=torch.float32, device=src.device) if want32 else None
+    o16 = torch.empty((M, W), dtype=torch.float16, device=src.device) if want16 else None
+    check(lib().ma_layernorm(ptr(x), ptr(res16), ptr(gamma), ptr(beta), eps, M, W, ptr(o32), ptr(o16), stream_ptr()),
+          "ma_layernorm")
+    return o32, o16
+
+
+def attention_f16(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, nkeys: torch.Tensor,
+                  slots: Optional[torch.Tensor] = None, scale: float = 0.125) -> torch.Tensor:
+    """q [M,H,64] fp16; k,v [S,H,T,64] fp16 (S cache slots); nkeys int32 [M]; slots int32 [M] or None (slot m)."""
+    _need_cuda(q, k, v, nkeys, slots)
+    M, H, D = q.shape
+    assert D == 64 and k.is_contiguous() and v.is_contiguous() and q.is_contiguous()
+    T = k.shape[2]
+    max_keys = int(nkeys.max().item())
+    scratch = torch.zeros(lib().ma_attention_scratch_bytes(M, H, max_keys), dtype=torch.uint8, device=q.device)
+    out = torch.empty((M, H, D), dtype=torch.float16, device=q.device)
+    check(lib().ma_attention_f16(ptr(q), H * D, ptr(k), ptr(v), T, H, ptr(slots), ptr(nkeys), max_keys, M, scale,
+                                 ptr(out), H * D, ptr(scratch), stream_ptr()), "ma_attention_f16")
+    return out

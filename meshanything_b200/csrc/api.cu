@@ -1,0 +1,331 @@
+// api.cu -- the C ABI of libmeshanything_b200.so (include/meshanything_b200.h) and the host side
+// of generate(): prefill, then one CUDA graph launch per token.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <vector>
+
+#include "canon.cuh"
+#include "internal.h"
+
+namespace ma {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += (unsigned long long)n; }
+bool check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- workspace carve-up of the decoder ---------------------------------------------------------
+constexpr int PREFILL_SEQS = 8;  // sequences prefilled per pass (rows = 257 * PREFILL_SEQS)
+
+struct DecWs {
+  float* hres;
+  __half *x16, *qkv, *attn16, *y16, *f16, *logits, *lastx16;
+  int* nkeys;
+  SeqState s;
+  int* all_done;
+  void* attn_scratch;
+  size_t attn_scratch_bytes;
+  void* fast;
+  size_t total;
+};
+
+static DecWs carve(void* base, int B, int tmax, int vocab) {
+  DecWs w;
+  const size_t rows = (size_t)std::max(B, PREFIX * std::min(B, PREFILL_SEQS));
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((char*)base + off) : nullptr;
+    off += align_up(bytes);
+    return p;
+  };
+  w.hres = (float*)take(rows * HID * 4);
+  w.x16 = (__half*)take(rows * HID * 2);
+  w.qkv = (__half*)take(rows * QKV * 2);
+  w.attn16 = (__half*)take(rows * HID * 2);
+  w.y16 = (__half*)take(rows * HID * 2);
+  w.f16 = (__half*)take(rows * FFN * 2);
+  w.logits = (__half*)take((size_t)B * vocab * 2);
+  w.lastx16 = (__half*)take((size_t)B * HID * 2);
+  w.nkeys = (int*)take(rows * 4);
+  w.s.pos = (int*)take((size_t)B * 4);
+  w.s.gen = (int*)take((size_t)B * 4);
+  w.s.tok = (int*)take((size_t)B * 4);
+  w.s.finished = (int*)take((size_t)B * 4);
+  w.s.lens = (int*)take((size_t)B * 4);
+  w.all_done = (int*)take(256);
+  w.attn_scratch_bytes = std::max(attention_scratch_bytes((int)B, NHEAD, tmax),
+                                  attention_scratch_bytes(PREFIX * std::min(B, PREFILL_SEQS), NHEAD, PREFIX));
+  w.attn_scratch = take(w.attn_scratch_bytes);
+  w.fast = take(fast_workspace_bytes());
+  w.total = off;
+  return w;
+}
+
+static inline __half* kv_layer(void* kv, int layer, int which, int B, long T) {
+  return (__half*)kv + ((size_t)(layer * 2 + which) * B) * NHEAD * T * HD;
+}
+
+// One pass of the 24 layers over M rows (general batched kernels).
+static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, int B, long T, int M, int rows_per_slot,
+                      int slot0, int max_keys, cudaStream_t st) {
+  for (int L = 0; L < w->n_layers; L++) {
+    __half* kc = kv_layer(kv, L, 0, B, T) + (size_t)slot0 * NHEAD * T * HD;
+    __half* vc = kv_layer(kv, L, 1, B, T) + (size_t)slot0 * NHEAD * T * HD;
+    if (launch_linear((const __half*)w->wqkv[L], (const __half*)w->bqkv[L], ws.x16, HID, ws.qkv, QKV, M, QKV, HID,
+                      MA_EPI_NONE, st)) return 1;
+    if (launch_kv_append(ws.qkv, M, rows_per_slot, ws.nkeys, kc, vc, T, st)) return 1;
+    if (launch_attention(ws.qkv, QKV, kc, vc, T, NHEAD, rows_per_slot, nullptr, ws.nkeys, max_keys, M, 0.125f,
+                         ws.attn16, HID, ws.attn_scratch, st)) return 1;
+    if (launch_linear((const __half*)w->wo[L], (const __half*)w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID,
+                      MA_EPI_NONE, st)) return 1;
+    if (launch_layernorm(ws.hres, ws.y16, w->ln1g[L], w->ln1b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
+    if (launch_linear((const __half*)w->w1[L], (const __half*)w->b1[L], ws.x16, HID, ws.f16, FFN, M, FFN, HID,
+                      MA_EPI_RELU, st)) return 1;
+    if (launch_linear((const __half*)w->w2[L], (const __half*)w->b2[L], ws.f16, FFN, ws.y16, HID, M, HID, FFN,
+                      MA_EPI_NONE, st)) return 1;
+    if (launch_layernorm(ws.hres, ws.y16, w->ln2g[L], w->ln2b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
+  }
+  return 0;
+}
+
+// ---- per-step CUDA graphs ----------------------------------------------------------------------
+struct GraphKey {
+  const void *w, *kv, *ws, *out_ids, *forced, *logits_out;
+  unsigned long long whash;
+  int B, tmax, max_new, bucket, flags, do_sample, top_k, eos, pad;
+  float top_p;
+  unsigned long long seed;
+  bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
+};
+static std::map<GraphKey, cudaGraphExec_t> g_graphs;
+static std::map<cudaGraphExec_t, unsigned long long> g_graph_launches;  // kernels per launch of a graph
+static cudaStream_t g_stream = nullptr;
+static int* g_flag_host = nullptr;  // pinned
+static cudaEvent_t g_ev_in = nullptr, g_ev_out = nullptr, g_ev_flag = nullptr;
+
+static int ensure_globals() {
+  if (!g_stream) {
+    if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void**)&g_flag_host, 64, cudaHostAllocDefault) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_ev_out, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&g_ev_flag, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("cannot create stream/events: %s", cudaGetErrorString(cudaGetLastError()));
+      return 1;
+    }
+  }
+  return 0;
+}
+
+}  // namespace ma
+
+using namespace ma;
+
+extern "C" {
+
+int ma_abi_version(void) { return MA_ABI_VERSION; }
+const char* ma_last_error(void) { return g_err; }
+unsigned long long ma_launch_count(void) { return g_launches.load(); }
+
+int ma_linear_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
+                  int epilogue, void* stream) {
+  return launch_linear((const __half*)W, (const __half*)bias, (const __half*)x, ldx, (__half*)y, ldy, M, N, K,
+                       epilogue, (cudaStream_t)stream);
+}
+
+int ma_layernorm(const float* x, const void* res16, const float* gamma, const float* beta, float eps, int M, int W,
+                 float* out32, void* out16, void* stream) {
+  return launch_layernorm(x, (const __half*)res16, gamma, beta, eps, M, W, out32, (__half*)out16,
+                          (cudaStream_t)stream);
+}
+
+size_t ma_attention_scratch_bytes(int M, int H, int max_keys) { return attention_scratch_bytes(M, H, max_keys); }
+
+int ma_attention_f16(const void* q, int ldq, const void* K, const void* V, long T, int H, const int* slots,
+                     const int* nkeys, int max_keys, int M, float scale, void* out, int ldo, void* scratch,
+                     void* stream) {
+  if (M > 65535) {
+    set_error("ma_attention_f16: M=%d exceeds 65535 rows per call", M);
+    return 1;
+  }
+  return launch_attention((const __half*)q, ldq, (const __half*)K, (const __half*)V, T, H, 1, slots, nkeys, max_keys, M,
+                          scale, (__half*)out, ldo, scratch, (cudaStream_t)stream);
+}
+
+size_t ma_kv_cache_bytes(int n_layers, int B, int tmax) {
+  return (size_t)n_layers * 2 * B * NHEAD * (size_t)tmax * HD * sizeof(__half);
+}
+
+size_t ma_decoder_workspace_bytes(int B, int tmax) { return carve(nullptr, B, tmax, 8195 + 61).total; }
+
+int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, int tmax, int max_new,
+                       const ma_sampling* sampling, int eos_id, int pad_id, void* kv, void* ws_, int32_t* out_ids,
+                       int32_t* out_lens, const int32_t* forced_ids, void* logits_out, int flags, void* stream) {
+  if (!w || !prefix || !kv || !ws_ || !out_ids || B <= 0 || max_new <= 0) {
+    set_error("ma_decode_generate: bad arguments");
+    return 1;
+  }
+  if (w->n_layers > MA_MAX_LAYERS || w->vocab > 8195 + 61) {
+    set_error("ma_decode_generate: n_layers=%d / vocab=%d unsupported", w->n_layers, w->vocab);
+    return 1;
+  }
+  if (PREFIX + max_new > tmax) {
+    set_error("ma_decode_generate: tmax=%d < 257 + max_new=%d", tmax, max_new);
+    return 1;
+  }
+  if (PREFIX + max_new + 2 > w->npos) {
+    // meshanything.py:97-98: 18259 learned positions (+2 offset rows)
+    set_error("ma_decode_generate: sequence of %d exceeds %d learned positions", PREFIX + max_new, w->npos - 2);
+    return 1;
+  }
+  if (ensure_globals()) return 1;
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t st = g_stream;  // graph capture is illegal on the legacy default stream: always run on our own
+  cudaEventRecord(g_ev_in, user);
+  cudaStreamWaitEvent(st, g_ev_in, 0);
+
+  const long T = tmax;
+  DecWs ws = carve(ws_, B, tmax, 8195 + 61);
+  cudaMemsetAsync(ws.attn_scratch, 0, ws.attn_scratch_bytes, st);
+  cudaMemsetAsync(ws.fast, 0, fast_workspace_bytes(), st);
+  if (launch_fill_i32(out_ids, pad_id, (long)B * max_new, st)) return 1;
+
+  SampleArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.logits = ws.logits; sa.vocab = w->vocab; sa.B = B; sa.max_new = max_new; sa.eos_id = eos_id; sa.pad_id = pad_id;
+  sa.do_sample = sampling ? sampling->do_sample : 0;
+  sa.top_k = sampling ? sampling->top_k : 0;
+  sa.top_p = sampling ? sampling->top_p : 1.0f;
+  sa.seed = sampling ? sampling->seed : 0;
+  sa.s = ws.s; sa.first = 1; sa.out_ids = out_ids; sa.forced = forced_ids; sa.logits_out = (__half*)logits_out;
+  sa.all_done = ws.all_done;
+
+  const bool fast = (B == 1) && !(flags & MA_GEN_NO_FAST);
+  if (fast) sa.nkeys_next = fast_nkeys_ptr(ws.fast);
+
+  // ---- prefill: 257 prefix rows per sequence, PREFILL_SEQS sequences per pass
+  for (int b0 = 0; b0 < B; b0 += PREFILL_SEQS) {
+    const int nb = std::min(PREFILL_SEQS, B - b0), M = nb * PREFIX;
+    if (launch_embed_prefix(w, prefix + (size_t)b0 * PREFIX * HID, nb, ws.hres, ws.x16, ws.nkeys, st)) return 1;
+    if (run_layers(w, ws, kv, B, T, M, PREFIX, b0, PREFIX, st)) return 1;
+    if (launch_gather_rows(ws.x16, HID, PREFIX - 1, PREFIX, nb, ws.lastx16 + (size_t)b0 * HID, st)) return 1;
+  }
+  if (launch_linear((const __half*)w->lm_head, nullptr, ws.lastx16, HID, ws.logits, w->vocab, B, w->vocab, HID,
+                    MA_EPI_NONE, st)) return 1;
+  if (launch_sample(sa, st)) return 1;
+  sa.first = 0;
+  sa.nkeys_next = nullptr;
+
+  // ---- decode: one step per generated token
+
+  const bool use_graph = !(flags & MA_GEN_NO_GRAPH);
+  const bool early = !(flags & MA_GEN_NO_EARLY_EXIT) && !forced_ids;
+  const int CHECK_EVERY = 64;
+  bool flag_pending = false;
+  int rc = 0;
+  for (int i = 1; i < max_new && rc == 0; i++) {
+    const int ctx = PREFIX + i;                          // keys visible to this step (all rows advance together)
+    const int bucket = fast ? 0 : (ctx + 1023) / 1024;   // attention grid size class (general path)
+    const int max_keys = fast ? tmax : std::min(tmax, bucket * 1024);
+    auto enqueue = [&](cudaStream_t s) -> int {
+      if (fast) return fast_step_enqueue(w, ws.s, tmax, (__half*)kv, ws.fast, sa, !(flags & MA_GEN_NO_PDL), s);
+      if (launch_embed_tokens(w, ws.s, B, ws.hres, ws.x16, ws.nkeys, s)) return 1;
+      if (run_layers(w, ws, kv, B, T, B, 1, 0, max_keys, s)) return 1;
+      if (launch_linear((const __half*)w->lm_head, nullptr, ws.x16, HID, ws.logits, w->vocab, B, w->vocab, HID,
+                        MA_EPI_NONE, s)) return 1;
+      return launch_sample(sa, s);
+    };
+    if (!use_graph) {
+      rc = enqueue(st);
+    } else {
+      GraphKey key;
+      memset(&key, 0, sizeof(key));
+      key.w = w; key.kv = kv; key.ws = ws_; key.out_ids = out_ids; key.forced = forced_ids; key.logits_out = logits_out;
+      key.B = B; key.tmax = tmax; key.max_new = max_new; key.bucket = bucket; key.flags = flags;
+      key.do_sample = sa.do_sample; key.top_k = sa.top_k; key.eos = eos_id; key.pad = pad_id; key.top_p = sa.top_p;
+      key.seed = sa.seed;
+      {  // the weights struct is read at capture time: key on its contents, not only its address
+        unsigned long long h = 1469598103934665603ull;
+        const unsigned char* pb = (const unsigned char*)w;
+        for (size_t q = 0; q < sizeof(ma_decoder_weights); q++) h = (h ^ pb[q]) * 1099511628211ull;
+        key.whash = h;
+      }
+      auto it = g_graphs.find(key);
+      if (it == g_graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+          set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(cudaGetLastError()));
+          return 1;
+        }
+        const unsigned long long before = g_launches.load();
+        int erc = enqueue(st);
+        const unsigned long long per_step = g_launches.load() - before;
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (erc || ce != cudaSuccess || !graph) {
+          if (!erc) set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+          cudaGetLastError();
+          return 1;
+        }
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+          set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+          return 1;
+        }
+        if (g_graphs.size() > 64) {
+          for (auto& kvp : g_graphs) cudaGraphExecDestroy(kvp.second);
+          g_graphs.clear();
+        }
+        it = g_graphs.emplace(key, exec).first;
+        g_launches -= per_step;  // the capture itself launched nothing
+        g_graph_launches[exec] = per_step;
+      }
+      if (cudaGraphLaunch(it->second, st) != cudaSuccess) {
+        set_error("cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
+        return 1;
+      }
+      g_launches += g_graph_launches[it->second];
+    }
+    if (early && (i % CHECK_EVERY) == 0) {
+      // lagged, non-blocking early-exit poll: look at the flag copied CHECK_EVERY steps ago
+      if (flag_pending && cudaEventQuery(g_ev_flag) == cudaSuccess) {
+        if (*g_flag_host == 1) break;
+        flag_pending = false;
+      }
+      if (!flag_pending) {
+        cudaMemcpyAsync(g_flag_host, ws.all_done, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(g_ev_flag, st);
+        flag_pending = true;
+      }
+    }
+  }
+  if (rc) return rc;
+  if (out_lens) cudaMemcpyAsync(out_lens, ws.s.lens, sizeof(int) * B, cudaMemcpyDeviceToDevice, st);
+  cudaEventRecord(g_ev_out, st);
+  cudaStreamWaitEvent(user, g_ev_out, 0);
+  return check_launch("ma_decode_generate") ? 0 : 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""-m gpu: ShapeOPT decoder generate() on the B200 against the CPU oracle (bit-exact ids AND fp16 logits)."""
+import pytest
+import torch
+
+from tests.util import decoder_sd, random_prefix
+
+gpu = pytest.mark.gpu
+NL = 3          # layers of the small synthetic decoder used by most cases
+NEW = 40        # new tokens of the short cases
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def small():
+    from meshanything_b200.decoder import DecoderArena
+    from oracle.decoder import OracleDecoder
+    sd = decoder_sd(NL)
+    arena = DecoderArena(sd, _dev())
+    oracle = OracleDecoder(sd, NL, 257 + 600)
+    return sd, arena, oracle
+
+
+@gpu
+def test_tok_table_matches_oracle(small):
+    _, arena, oracle = small
+    assert torch.equal(arena.tok_table.cpu().view(torch.int16), oracle.tok_table().view(torch.int16))
+
+
+@gpu
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 2 | 1])
+def test_greedy_bit_exact_vs_oracle(small, flags):
+    """free-running greedy decode: token ids and every step's fp16 logits equal the oracle's."""
+    from meshanything_b200.decoder import Generator
+    _, arena, oracle = small
+    prefix = random_prefix(1, seed=3)
+    gen = Generator(arena, 1, 257 + NEW)
+    ids, lens, logits = gen.generate(prefix.to(_dev()), NEW, want_logits=True, flags=flags)
+    torch.cuda.synchronize()
+    ref_ids, ref_logits = oracle.generate(prefix[0], NEW, keep_logits=True)
+    assert ids[0].cpu().tolist() == ref_ids
+    for i, rl in enumerate(ref_logits):
+        assert torch.equal(logits[i, 0].cpu().view(torch.int16), rl.view(torch.int16)), f"logits differ at step {i}"
+    assert int(lens[0]) == NEW
+
+
+@gpu
+def test_batch_invariance_and_batched_parity(small):
+    """a batch of 5 gives, row by row, what each sequence gives alone (and what the oracle gives)."""
+    from meshanything_b200.decoder import Generator
+    _, arena, oracle = small
+    B = 5
+    prefix = random_prefix(B, seed=11)
+    gen = Generator(arena, B, 257 + NEW)
+    ids, lens = gen.generate(prefix.to(_dev()), NEW)
+    torch.cuda.synchronize()
+    single = Generator(arena, 1, 257 + NEW)
+    for b in range(B):
+        one, _ = single.generate(prefix[b:b + 1].to(_dev()), NEW)
+        assert ids[b].cpu().tolist() == one[0].cpu().tolist()
+    for b in (0, B - 1):
+        ref_ids, _ = oracle.generate(prefix[b], NEW)
+        assert ids[b].cpu().tolist() == ref_ids
+
+
+@gpu
+def test_prefill_larger_than_one_pass(small):
+    """more sequences than one prefill pass (8) takes."""
+    from meshanything_b200.decoder import Generator
+    _, arena, oracle = small
+    B = 10
+    prefix = random_prefix(B, seed=21)
+    gen = Generator(arena, B, 257 + 6)
+    ids, _ = gen.generate(prefix.to(_dev()), 6)
+    ref_ids, _ = oracle.generate(prefix[9], 6)
+    assert ids[9].cpu().tolist() == ref_ids
+
+
+@gpu
+def test_eos_and_padding(small):
+    """HF semantics: a row that emitted eos is padded; generation stops early when all rows finished."""
+    from meshanything_b200.decoder import Generator
+    _, arena, oracle = small
+    prefix = random_prefix(2, seed=5)
+    gen = Generator(arena, 2, 257 + NEW)
+    free, _ = gen.generate(prefix.to(_dev()), NEW)
+    free = free.cpu()
+    eos = int(free[0, 7])                     # pretend the 8th token of row 0 is eos
+    first0 = free[0].tolist().index(eos)
+    ids, lens = gen.generate(prefix.to(_dev()), NEW, eos_id=eos, pad_id=2)
+    ids, lens = ids.cpu(), lens.cpu()
+    assert ids[0, :first0 + 1].tolist() == free[0, :first0 + 1].tolist()
+    assert all(t == 2 for t in ids[0, first0 + 1:].tolist())
+    assert int(lens[0]) == first0 + 1
+    row1 = free[1].tolist()
+    if eos in row1:
+        j = row1.index(eos)
+        assert ids[1, :j + 1].tolist() == row1[:j + 1] and int(lens[1]) == j + 1
+    else:
+        assert ids[1].tolist() == row1 and int(lens[1]) == NEW
+    # batch of one (fast path): stops at eos, remaining ids are pad, oracle agrees
+    g1 = Generator(arena, 1, 257 + NEW)
+    ids1, lens1 = g1.generate(prefix[:1].to(_dev()), NEW, eos_id=eos)
+    ref_ids, _ = oracle.generate(prefix[0], NEW, eos_id=eos)
+    got = ids1[0].cpu().tolist()
+    assert got[:len(ref_ids)] == ref_ids and all(t == 2 for t in got[len(ref_ids):])
+    assert int(lens1[0]) == len(ref_ids)
+
+
+@gpu
+def test_teacher_forced_logits(small):
+    """forced ids (incl. specials 0/1/2, which take the extra_embeds path) give the oracle's logits."""
+    from meshanything_b200.decoder import Generator
+    _, arena, oracle = small
+    prefix = random_prefix(1, seed=8)
+    forced = [0, 5, 8194, 1, 2, 3, 77, 4000, 2, 9, 10, 11, 12]
+    n = len(forced)
+    for flags in (0, 2):
+        gen = Generator(arena, 1, 257 + n)
+        f = torch.tensor([forced], dtype=torch.int32)
+        ids, lens, logits = gen.generate(prefix.to(_dev()), n, forced_ids=f, want_logits=True, eos_id=-1, flags=flags)
+        _, ref_logits = oracle.generate(prefix[0], n, eos_id=-1, forced=forced, keep_logits=True)
+        assert ids[0].cpu().tolist() == forced
+        for i in range(n):
+            assert torch.equal(logits[i, 0].cpu().view(torch.int16), ref_logits[i].view(torch.int16)), (flags, i)
+
+
+@gpu
+def test_long_context_crosses_chunks(small):
+    """600 new tokens: the context crosses three 256-key attention chunks (257 -> 857)."""
+    from meshanything_b200.decoder import Generator
+    _, arena, oracle = small
+    prefix = random_prefix(1, seed=13)
+    n = 600
+    gen = Generator(arena, 1, 257 + n)
+    ids, _ = gen.generate(prefix.to(_dev()), n)
+    ref_ids, _ = oracle.generate(prefix[0], n)
+    assert ids[0].cpu().tolist() == ref_ids
+
+
+@gpu
+def test_sampling_is_deterministic_and_in_support(small):
+    from meshanything_b200.decoder import Generator
+    _, arena, _ = small
+    prefix = random_prefix(2, seed=17)
+    gen = Generator(arena, 2, 257 + 24)
+    a, _, lg = gen.generate(prefix.to(_dev()), 24, do_sample=True, seed=7, want_logits=True)
+    b, _ = gen.generate(prefix.to(_dev()), 24, do_sample=True, seed=7)
+    c, _ = gen.generate(prefix.to(_dev()), 24, do_sample=True, seed=8)
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
+    # every sampled token is inside the reference's top-k(50) support of that step's logits
+    for i in range(24):
+        for r in range(2):
+            top = torch.topk(lg[i, r].float(), 50).values[-1]
+            assert lg[i, r, int(a[r, i])].float() >= top
+
+
+@gpu
+@pytest.mark.slow
+def test_full_depth_config1_golden():
+    """24 layers, F=64 (578 new tokens): ids equal the oracle's; cross-checked with the committed golden."""
+    import json, os
+    from meshanything_b200.decoder import DecoderArena, Generator
+    from oracle.decoder import OracleDecoder
+    sd = decoder_sd(24)
+    arena = DecoderArena(sd, _dev())
+    prefix = random_prefix(1, seed=1)
+    n = 64 * 9 + 2
+    gen = Generator(arena, 1, 257 + n)
+    ids, _ = gen.generate(prefix.to(_dev()), n)
+    got = ids[0].cpu().tolist()
+    gold = os.path.join(os.path.dirname(__file__), "golden", "decoder_greedy_seed0_F64.json")
+    if os.path.exists(gold):
+        assert got == json.load(open(gold))["ids"]
+    else:
+        oracle = OracleDecoder(sd, 24, 257 + n)
+        ref, _ = oracle.generate(prefix[0], n)
+        assert got == ref
