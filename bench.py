@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py -- face-tokens/sec of the MeshAnything-350M hot path on B200 (BASELINE.json metric).
+
+One "step" = one full pass of the hot path over one batch of synthetic inputs: generate()
+of `--faces`*9+2 tokens for `--batch` shapes per GPU (default: BASELINE.json configs[1] = batch 1,
+800-face cap, greedy).  Weak scaling: every rank runs the same per-GPU batch on its own shapes;
+the only collective is the weight broadcast at init.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--faces F] [--sampling]
+    python bench.py --impl reference ...      # the CPU oracle on the host cores (bounded sample)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "face-tokens/sec (350M, 800-face cap)"
+UNIT = "tokens/s"
+KV_BYTES_PER_POS = 98304          # 24 layers x K,V x 1024 x fp16  
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) >= 8 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) >= 8 and r[2].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_prefix(batch: int, first: int) -> torch.Tensor:
+    """Stand-in for processed_point_feature while the encoder leg is timed separately: fp32 [B,257,1024],
+    shape i seeded with 1000+i."""
+    rows = []
+    for i in range(batch):
+        g = torch.Generator().manual_seed(1000 + first + i)
+        rows.append(torch.randn(257, 1024, generator=g) * 0.7)
+    return torch.stack(rows)
+
+
+def cpu_oracle_tokens_per_s(sd, n_layers: int, seconds: float = 12.0):
+    """The oracle (CPU restatement of the reference decoder) on the host cores: prefill + as many greedy
+    decode steps as fit in ~`seconds`.  Reported baseline only."""
+    from oracle.decoder import OracleDecoder, greedy_pick
+    cores = os.cpu_count() or 1
+    oracle = OracleDecoder(sd, n_layers, 257 + 4096)
+    prefix = synthetic_prefix(1, 0)[0]
+    t0 = time.time()
+    logits = oracle.prefill(prefix)
+    t_prefill = time.time() - t0
+    n, t1 = 0, time.time()
+    tok = greedy_pick(logits)
+    while time.time() - t1 < seconds and n < 4000:
+        logits = oracle.step(tok, n + 1)
+        tok = greedy_pick(logits)
+        n += 1
+    dt = time.time() - t1
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"oracle/decoder_oracle.c: 257-token prefill ({t_prefill:.2f}s, not counted) + {n} greedy "
+                      f"decode steps at context 257..{257 + n} in {dt:.1f}s, batch 1, {n_layers} layers, "
+                      f"OpenMP on {cores} cores"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="shapes per GPU")
+    ap.add_argument("--faces", type=int, default=800)
+    ap.add_argument("--layers", type=int, default=24)
+    ap.add_argument("--sampling", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    from meshanything_b200 import parallel
+    from meshanything_b200.checkpoint import decoder_specs, make_state_dict
+    from meshanything_b200.config import DEC
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    F, B, NL = args.faces, args.batch, args.layers
+    max_new = DEC.max_new_tokens(F)
+    face_tokens_per_seq = 9 * F
+    workload = f"350M ({NL} layers), batch={B}/GPU, {F}-face cap ({max_new} new tokens), " + (
+        "top-k 50 / top-p 0.95 sampling" if args.sampling else "greedy decode")
+
+    specs = decoder_specs(NL)
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sd = make_state_dict(specs, 0)
+        vals = []
+        base = None
+        for _ in range(max(1, args.warmup > 0) + args.steps):
+            base = cpu_oracle_tokens_per_s(sd, NL, seconds=8.0)
+            vals.append(base["value"])
+        vals = vals[-args.steps:]
+        v = sum(vals) / len(vals)
+        base["value"] = v
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 weights/activations, f32 accumulate", "data": "synthetic",
+            "config": {"workload": workload, "note": "bounded sample of the same workload on the host cores"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    rank, world, local = parallel.init_from_env()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    from meshanything_b200 import capi
+    from meshanything_b200.decoder import DecoderArena, Generator
+
+    sd_host = make_state_dict(specs, 0) if rank == 0 else None
+    sd = parallel.broadcast_state_dict(sd_host, specs, dev)      # one NCCL broadcast, no collective in the step
+    arena = DecoderArena(sd, dev, n_layers=NL)
+    del sd
+    tmax = 257 + max_new
+    gen = Generator(arena, B, tmax)
+    flags = args.flags | capi.GEN_NO_EARLY_EXIT
+    prefix_host = synthetic_prefix(B, rank * B).pin_memory()
+    prefix_dev = prefix_host.to(dev)
+
+    def one_step_resident():
+        return gen.generate(prefix_dev, max_new, do_sample=args.sampling, seed=0, flags=flags)
+
+    def one_step_e2e():
+        p = prefix_host.to(dev, non_blocking=True)
+        ids, lens = gen.generate(p, max_new, do_sample=args.sampling, seed=0, flags=flags)
+        return ids.to("cpu", non_blocking=False), lens
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    for _ in range(args.warmup):
+        one_step_resident()
+    launches0 = capi.lib().ma_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, out = timed(one_step_resident, args.steps)
+    clocks = sampler.stop()
+    launches = capi.lib().ma_launch_count() - launches0
+    ms_e2e, out_e2e = timed(one_step_e2e, args.steps)
+
+    ids = out[0]
+    n_tokens = world * B * face_tokens_per_seq * args.steps
+    value = n_tokens / (ms / 1000.0)
+    e2e_value = n_tokens / (ms_e2e / 1000.0)
+
+    # ---- roofline of the decode step (the HBM-bound part): algorithmic bytes per token-step / time per step
+    peak, peak_src = measured_peaks()
+    wbytes = arena.weight_bytes_per_step()
+    n_dec = max_new - 1                                           # decode steps per generate (step 0 is the prefill)
+    kv_read = sum(KV_BYTES_PER_POS * (257 + i) for i in range(1, max_new)) * B
+    kv_write = KV_BYTES_PER_POS * n_dec * B
+    alg_bytes_per_gen = wbytes * n_dec + kv_read + kv_write
+    # short-context GEMV-dominated slice: (T(300 tokens) - T(100 tokens)) / 200 steps
+    def short(nn):
+        g2 = Generator(arena, B, tmax)
+        for _ in range(2):
+            g2.generate(prefix_dev, nn, flags=flags)
+        t, _ = timed(lambda: g2.generate(prefix_dev, nn, flags=flags), 3)
+        return t / 3
+    t100, t300 = short(100), short(300)
+    us_step_short = (t300 - t100) / 200.0 * 1000.0
+    short_bytes = wbytes + KV_BYTES_PER_POS * B * (257 + 200 + 1)
+    t_prefill_ms = t100 - 99 * us_step_short / 1000.0
+    dec_ms = ms / args.steps - max(0.0, t_prefill_ms)             # decode-loop part of one generate
+    achieved = alg_bytes_per_gen / (dec_ms / 1000.0) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "decode step = 97 fast_gemv_kernel + 24 attention_kernel launches (one CUDA graph)"
+        if B == 1 else "decode step (gemm_canon + attention kernels, one CUDA graph)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": None,
+        "algorithmic_bytes_per_launch": alg_bytes_per_gen / n_dec,
+        "launch": "one decode step (graph launch); bytes = fp16 weights %d + KV read/write averaged over the run" % wbytes,
+        "us_per_step_avg": dec_ms * 1000.0 / n_dec,
+        "short_context": {"us_per_step": us_step_short, "bytes_per_step": short_bytes,
+                          "achieved": short_bytes / us_step_short / 1e3, "frac": short_bytes / us_step_short / 1e3 / peak,
+                          "note": "steps at context ~357..557 (GEMV-dominated): (T(300)-T(100))/200"},
+        "prefill_ms": t_prefill_ms,
+    }
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_oracle_tokens_per_s(make_state_dict(specs, 0), NL)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 weights/activations, f32 accumulate", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world} (batch sharded, "
+                       "weights broadcast once over NCCL)", "inputs": "prefix resident in HBM",
+                       "l2": "inputs larger than L2: 623.5 MB of weights + KV streamed per token (L2 = 126 MB)",
+                       "checkpoint": "synthetic seed 0 (random weights: no early EOS, every sequence runs the cap)"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(prefix_host.numel() * 4),
+                    "d2h_bytes_per_step": int(out_e2e[0].numel() * 4),
+                    "api": "meshanything_b200.decoder.Generator.generate (decoder leg of MeshAnything.forward)"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "check": {"first_ids": ids[0, :8].cpu().tolist()},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
