@@ -51,11 +51,14 @@ def decoder_specs(n_layers: int = DEC.n_layers) -> Dict[str, Spec]:
     d[f"{p}.cond_embed.weight"] = ((2, h), "normal", 0.1)
     for i in range(n_layers):
         q = f"{p}.layers.{i}"
-        for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+        for proj in ("q_proj", "k_proj", "v_proj"):
             _linear(d, f"{q}.self_attn.{proj}", h, h, 0.03)
+        # small out_proj / fc2 keep the residual stream input-dependent through 24 post-LN layers, so
+        # that greedy decoding of the random model does not collapse to one repeated token
+        _linear(d, f"{q}.self_attn.out_proj", h, h, 0.01)
         _ln(d, f"{q}.self_attn_layer_norm", h)
         _linear(d, f"{q}.fc1", DEC.ffn, h, 0.03)
-        _linear(d, f"{q}.fc2", h, DEC.ffn, 0.02)
+        _linear(d, f"{q}.fc2", h, DEC.ffn, 0.007)
         _ln(d, f"{q}.final_layer_norm", h)
     # meshanything.py:118 creates zeros; a trained checkpoint holds the VQ codebook here.
     d[f"{p}.quantize_codebooks"] = ((1, DEC.codebook_size, DEC.codebook_dim), "normal", 1.0)
