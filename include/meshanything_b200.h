@@ -111,6 +111,76 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
 #define MA_GEN_NO_FAST 2    /* batch-1: use the general batched kernels instead of the fused GEMV path */
 #define MA_GEN_NO_PDL 4     /* batch-1 fast path without programmatic dependent launch */
 #define MA_GEN_NO_EARLY_EXIT 8
+#define MA_GEN_NO_MEGA 16    /* batch-1 greedy: per-phase kernels (decode_fast.cu) instead of the persistent kernel */
+#define MA_GEN_TRACE 32      /* persistent kernel records globaltimer stamps of CTA 0 at every phase boundary */
+
+/* Debug read-back (synchronises the device): what = 0 -> int error flag of the persistent kernel (1 = a grid
+ * barrier timed out), what = 1 -> its uint64 trace stamps. */
+int ma_decoder_debug(void* ws, int B, int tmax, int what, void* host_out, int nbytes);
+
+
+/* ---- Michelangelo point-cloud encoder (a1-a8) ----------------------------------------------- */
+
+typedef struct { /* ResidualAttentionBlock, transformer_blocks.py:77-115 (qkv_bias: false) */
+  const void* c_qkv_w;            /* fp16 [2304][768] */
+  const void *c_proj_w, *c_proj_b; /* fp16 [768][768], [768] */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const void *fc_w, *fc_b;        /* fp16 [3072][768], [3072] */
+  const void *proj_w, *proj_b;    /* fp16 [768][3072], [768] */
+} ma_miche_block;
+
+typedef struct {
+  const void *input_proj_w, *input_proj_b; /* fp16 [768][256] (54 input columns, zero padded), [768] */
+  const float* query;                      /* fp32 [257][768]  sal_perceiver.py:42 */
+  const void *cq_w, *ckv_w;                /* fp16 [768][768], [1536][768]  (no bias) */
+  const void *cproj_w, *cproj_b;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *ln3_g, *ln3_b;
+  const void *fc_w, *fc_b, *proj_w, *proj_b;
+  ma_miche_block enc[8];                   /* encoder.self_attn.resblocks */
+  const float *lnpost_g, *lnpost_b;
+  const void *pre_kl_w, *pre_kl_b;         /* fp16 [128][768] */
+  const void *post_kl_w, *post_kl_b;       /* fp16 [768][256] (64 input columns, zero padded) */
+  ma_miche_block dec[16];                  /* transformer.resblocks */
+  const void *cond_head_w, *cond_head_b;   /* fp16 [1024][768]   meshanything.py:120 */
+  const void *cond_w, *cond_b;             /* fp16 [1024][1536]  meshanything.py:121 */
+} ma_encoder_weights;
+
+size_t ma_encoder_workspace_bytes(int B);
+
+/* point_encoder.encode_latents + MeshAnything.process_point_feature (meshanything.py:137-138):
+ * pc_normal fp16 [B][4096][6] -> point_feature fp32 [B][257][768], prefix fp32 [B][257][1024]. */
+int ma_encoder_forward(const ma_encoder_weights* w, const void* pc_normal, int B, float* point_feature, float* prefix,
+                       void* ws, void* stream);
+
+/* ---- VQ detokenizer (a17-a18) ------------------------------------------------------------------ */
+
+typedef struct { /* BERT layer in optimum-BetterTransformer spelling */
+  const void *in_w, *in_b;     /* fp16 [2304][768], [2304] */
+  const void *out_w, *out_b;   /* fp16 [768][768], [768] */
+  const void *l1_w, *l1_b;     /* fp16 [3072][768], [3072] */
+  const void *l2_w, *l2_b;     /* fp16 [768][3072], [768] */
+  const float *n1_g, *n1_b, *n2_g, *n2_b;
+} ma_bert_layer;
+
+typedef struct {
+  int n_layers;
+  ma_bert_layer layer[8];
+  const float* pos_embedding;  /* fp32 [18000][768] */
+  const float* point_pe;       /* fp32 [257][768] */
+  const float *ln_g, *ln_b, *pln_g, *pln_b;
+  const void *cond_w, *cond_b, *cond_head_w, *cond_head_b; /* fp16 [768][768] */
+  const void *down_w, *down_b; /* fp16 [768][3072] project_down_codebook */
+  const void *coor_w, *coor_b; /* fp16 [1152][768] to_coor_logits.0 */
+  const float* codebook;       /* fp32 [8192][1024] quantize_codebooks[0] */
+} ma_tokenizer_weights;
+
+size_t ma_detokenize_workspace_bytes(int B, int F);
+
+/* ids post-processing + get_codes + NoiseResistantDecoder (meshanything.py:163-174): gen_ids int32
+ * [B][max_new] = raw generate() output, max_new = 9F+2; -> out_xyz fp32 [B][F][3][3] (NaN rows = absent
+ * faces); ids_out optional int32 [B][9F] = the post-processed ids (-1 = absent). */
+int ma_detokenize(const ma_tokenizer_weights* w, const int32_t* gen_ids, int max_new, int B, int F,
+                  const float* point_feature, float* out_xyz, int32_t* ids_out, void* ws, void* stream);
 
 /* number of kernels launched by the library since load (bench.py's gpu_launches) */
 unsigned long long ma_launch_count(void);

@@ -15,7 +15,7 @@ from . import build as _build
 
 MA_MAX_LAYERS = 32
 EPI_NONE, EPI_RELU, EPI_GELU = 0, 1, 2
-GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT = 1, 2, 4, 8
+GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT, GEN_NO_MEGA, GEN_TRACE = 1, 2, 4, 8, 16, 32
 
 _vp = C.c_void_p
 
@@ -38,7 +38,8 @@ _lib = None
 EXPORTS = [
     "ma_abi_version", "ma_last_error", "ma_launch_count", "ma_linear_f16", "ma_layernorm",
     "ma_attention_scratch_bytes", "ma_attention_f16", "ma_kv_cache_bytes", "ma_decoder_workspace_bytes",
-    "ma_decode_generate",
+    "ma_decode_generate", "ma_decoder_debug", "ma_encoder_workspace_bytes", "ma_encoder_forward",
+    "ma_detokenize_workspace_bytes", "ma_detokenize",
 ]
 
 
@@ -70,6 +71,13 @@ def lib():
     L.ma_decoder_workspace_bytes.restype = C.c_size_t
     L.ma_decode_generate.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.POINTER(Sampling),
                                      C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]
+    L.ma_decoder_debug.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int]
+    L.ma_encoder_workspace_bytes.argtypes = [C.c_int]
+    L.ma_encoder_workspace_bytes.restype = C.c_size_t
+    L.ma_encoder_forward.argtypes = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]
+    L.ma_detokenize_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    L.ma_detokenize_workspace_bytes.restype = C.c_size_t
+    L.ma_detokenize.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]
     if L.ma_abi_version() != 1:
         raise RuntimeError("libmeshanything_b200.so: ABI version mismatch")
     _lib = L

@@ -47,6 +47,7 @@ struct DecWs {
   void* attn_scratch;
   size_t attn_scratch_bytes;
   void* fast;
+  void* mega;
   size_t total;
 };
 
@@ -78,6 +79,7 @@ static DecWs carve(void* base, int B, int tmax, int vocab) {
                                   attention_scratch_bytes(PREFIX * std::min(B, PREFILL_SEQS), NHEAD, PREFIX));
   w.attn_scratch = take(w.attn_scratch_bytes);
   w.fast = take(fast_workspace_bytes());
+  w.mega = take(mega_workspace_bytes());
   w.total = off;
   return w;
 }
@@ -222,7 +224,12 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   sa.all_done = ws.all_done;
 
   const bool fast = (B == 1) && !(flags & MA_GEN_NO_FAST);
+  const bool mega = fast && !sa.do_sample && !(flags & MA_GEN_NO_MEGA);
   if (fast) sa.nkeys_next = fast_nkeys_ptr(ws.fast);
+  if (mega && mega_prepare(w, ws.mega, st)) {
+    set_error("mega_prepare failed");
+    return 1;
+  }
 
   // ---- prefill: 257 prefix rows per sequence, PREFILL_SEQS sequences per pass
   for (int b0 = 0; b0 < B; b0 += PREFILL_SEQS) {
@@ -244,7 +251,16 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   const int CHECK_EVERY = 64;
   bool flag_pending = false;
   int rc = 0;
-  for (int i = 1; i < max_new && rc == 0; i++) {
+  if (mega) {
+    // persistent kernel: up to MEGA_STEPS tokens per launch; it returns early once the row has finished
+    const int MEGA_STEPS = 512;
+    int slot = 0;
+    for (int i = 1; i < max_new && rc == 0; i += MEGA_STEPS, slot ^= 1) {
+      rc = mega_enqueue(w, ws.s, tmax, (__half*)kv, ws.mega, sa, std::min(MEGA_STEPS, max_new - i), slot,
+                        (flags & MA_GEN_TRACE) ? 1 : 0, st);
+    }
+  }
+  for (int i = 1; i < max_new && rc == 0 && !mega; i++) {
     const int ctx = PREFIX + i;                          // keys visible to this step (all rows advance together)
     const int bucket = fast ? 0 : (ctx + 1023) / 1024;   // attention grid size class (general path)
     const int max_keys = fast ? tmax : std::min(tmax, bucket * 1024);
@@ -326,6 +342,14 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   cudaEventRecord(g_ev_out, st);
   cudaStreamWaitEvent(user, g_ev_out, 0);
   return check_launch("ma_decode_generate") ? 0 : 1;
+}
+
+
+int ma_decoder_debug(void* ws_, int B, int tmax, int what, void* host_out, int nbytes) {
+  DecWs ws = carve(ws_, B, tmax, 8195 + 61);
+  cudaDeviceSynchronize();
+  const char* src = (const char*)ws.mega + (what == 0 ? mega_error_flag_offset() : mega_trace_offset());
+  return cudaMemcpy(host_out, src, (size_t)nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 
 }  // extern "C"

@@ -119,3 +119,17 @@ class Generator:
                                            flags, capi.stream_ptr())
         capi.check(rc, "ma_decode_generate")
         return (ids, lens, logits) if want_logits else (ids, lens)
+
+    def mega_error(self) -> int:
+        """1 if a grid barrier of the persistent decode kernel timed out (synchronises the device)."""
+        out = C.c_int(0)
+        capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 0, C.byref(out), 4),
+                   "ma_decoder_debug")
+        return out.value
+
+    def mega_trace(self, n: int = 160):
+        """globaltimer stamps (ns) of CTA 0 at the phase boundaries of the last traced launch."""
+        buf = (C.c_uint64 * n)()
+        capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 1, buf, 8 * n),
+                   "ma_decoder_debug")
+        return list(buf)

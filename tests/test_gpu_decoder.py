@@ -30,15 +30,17 @@ def test_tok_table_matches_oracle(small):
 
 
 @gpu
-@pytest.mark.parametrize("flags", [0, 1, 2, 4, 2 | 1])
+@pytest.mark.parametrize("flags", [0, 16, 16 | 4, 16 | 1, 2, 2 | 1])
 def test_greedy_bit_exact_vs_oracle(small, flags):
-    """free-running greedy decode: token ids and every step's fp16 logits equal the oracle's."""
+    """free-running greedy decode: token ids and every step's fp16 logits equal the oracle's.
+    flags: 0 persistent kernel, 16 per-phase kernels + PDL, 16|4 without PDL, |1 without CUDA graph, 2 batched kernels."""
     from meshanything_b200.decoder import Generator
     _, arena, oracle = small
     prefix = random_prefix(1, seed=3)
     gen = Generator(arena, 1, 257 + NEW)
     ids, lens, logits = gen.generate(prefix.to(_dev()), NEW, want_logits=True, flags=flags)
     torch.cuda.synchronize()
+    assert gen.mega_error() == 0
     ref_ids, ref_logits = oracle.generate(prefix[0], NEW, keep_logits=True)
     assert ids[0].cpu().tolist() == ref_ids
     for i, rl in enumerate(ref_logits):
@@ -117,7 +119,7 @@ def test_teacher_forced_logits(small):
     prefix = random_prefix(1, seed=8)
     forced = [0, 5, 8194, 1, 2, 3, 77, 4000, 2, 9, 10, 11, 12]
     n = len(forced)
-    for flags in (0, 2):
+    for flags in (0, 16, 2):
         gen = Generator(arena, 1, 257 + n)
         f = torch.tensor([forced], dtype=torch.int32)
         ids, lens, logits = gen.generate(prefix.to(_dev()), n, forced_ids=f, want_logits=True, eos_id=-1, flags=flags)
@@ -134,10 +136,12 @@ def test_long_context_crosses_chunks(small):
     _, arena, oracle = small
     prefix = random_prefix(1, seed=13)
     n = 600
-    gen = Generator(arena, 1, 257 + n)
-    ids, _ = gen.generate(prefix.to(_dev()), n)
     ref_ids, _ = oracle.generate(prefix[0], n)
-    assert ids[0].cpu().tolist() == ref_ids
+    for flags in (0, 16):
+        gen = Generator(arena, 1, 257 + n)
+        ids, _ = gen.generate(prefix.to(_dev()), n, flags=flags)
+        assert ids[0].cpu().tolist() == ref_ids, flags
+        assert gen.mega_error() == 0
 
 
 @gpu
