@@ -254,9 +254,8 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   if (mega) {
     // persistent kernel: up to MEGA_STEPS tokens per launch; it returns early once the row has finished
     const int MEGA_STEPS = 512;
-    int slot = 0;
-    for (int i = 1; i < max_new && rc == 0; i += MEGA_STEPS, slot ^= 1) {
-      rc = mega_enqueue(w, ws.s, tmax, (__half*)kv, ws.mega, sa, std::min(MEGA_STEPS, max_new - i), slot,
+    for (int i = 1; i < max_new && rc == 0; i += MEGA_STEPS) {
+      rc = mega_enqueue(w, ws.s, tmax, (__half*)kv, ws.mega, sa, std::min(MEGA_STEPS, max_new - i), i - 1,
                         (flags & MA_GEN_TRACE) ? 1 : 0, st);
     }
   }

@@ -76,7 +76,7 @@ int fast_step_enqueue(const ma_decoder_weights* w, SeqState s, int tmax, __half*
 size_t mega_workspace_bytes();
 int mega_prepare(const ma_decoder_weights* w, void* mega_ws, cudaStream_t st);
 int mega_enqueue(const ma_decoder_weights* w, SeqState s, int tmax, __half* kv, void* mega_ws, const SampleArgs& sa,
-                 int n_steps, int bar_slot, int trace, cudaStream_t st);
+                 int n_steps, int step_base, int trace, cudaStream_t st);
 int mega_error_flag_offset();
 int mega_trace_offset();
 

@@ -1,5 +1,5 @@
-"""Phase timeline of the persistent decode kernel (CTA 0, globaltimer): python tools_trace.py [faces]"""
-import sys, torch
+"""Phase timeline of the persistent decode kernel (CTA 0, globaltimer): python tools_trace.py [new_tokens]"""
+import sys, torch, collections
 sys.path.insert(0, '.')
 from meshanything_b200 import capi
 from meshanything_b200.checkpoint import decoder_specs, make_state_dict
@@ -16,17 +16,17 @@ for _ in range(2):
 gen.generate(p, n, flags=capi.GEN_NO_EARLY_EXIT | capi.GEN_TRACE)
 torch.cuda.synchronize()
 print('error flag', gen.mega_error())
-tr = gen.mega_trace(150)
-t0 = tr[0]
-names = ['qkv', 'attn', 'out', 'fc1', 'fc2']
-# stamps: step start, then 5 per layer, then after pick
-d = [(tr[i + 1] - tr[i]) / 1000.0 for i in range(0, 1 + 5 * NL)]
-import collections
+tr = gen.mega_trace(1280)
+# per layer stamps: [qkv: prologue_done, weights_ready, compute+refill done, barrier done], attn, out, fc1, fc2 (1 each)
+per_layer = 6
+names = ['qkv.prologue', 'qkv.compute', 'attn', 'out', 'fc1', 'fc2']
 agg = collections.defaultdict(list)
-for i in range(5 * NL):
-    agg[names[i % 5]].append(d[i])
+i = 1
+for L in range(NL):
+    for k in range(per_layer):
+        agg[names[k]].append((tr[i] - tr[i - 1]) / 1000.0)
+        i += 1
 for k in names:
     v = agg[k]
-    print(f'{k:5s} avg {sum(v)/len(v):6.2f} us  min {min(v):6.2f} max {max(v):6.2f}')
-print('lm+pick', d[5 * NL], 'us; step total', (tr[1 + 5 * NL] - tr[0]) / 1000.0, 'us')
-print('second step total', (tr[2 * (1 + 5 * NL) ] - tr[1 + 5 * NL]) / 1000.0 if len(tr) > 2 * (1 + 5 * NL) else None)
+    print(f'{k:14s} avg {sum(v)/len(v):6.2f} us  min {min(v):6.2f} max {max(v):6.2f}')
+print('lm+pick', (tr[i] - tr[i - 1]) / 1000.0, 'us; step total', (tr[i] - tr[0]) / 1000.0, 'us')
