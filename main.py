@@ -1,0 +1,158 @@
+"""Drop-in for /root/reference/main.py (same flags, same outputs) on top of the B200-native MeshAnything.
+
+    python main.py --input_type pc_normal --input_path pc_examples/mouse.npy --out_dir out [--sampling]
+    torchrun --nproc-per-node 8 main.py --input_type pc_normal --input_dir pcs --batchsize_per_gpu 64
+
+Differences forced by the environment: no accelerate / hf_hub (there is no network) -- one process per
+GPU is launched with torchrun, batches are dealt round-robin to the ranks as accelerate's prepared
+DataLoader does (main.py:146), and weights come from `--pretrained_weights` (a local safetensors file
+with the published keys) or, with `--pretrained_weights synthetic`, from the seeded random checkpoint.
+"""
+import argparse
+import datetime
+import os
+import time
+
+import numpy as np
+import torch
+
+from MeshAnything.models.meshanything import MeshAnything
+from mesh_to_pc import load_mesh, process_mesh_to_pc
+
+
+class Dataset:
+    def __init__(self, input_type, input_list, mc=False):
+        super().__init__()
+        self.data = []
+        if input_type == 'pc_normal':
+            for input_path in input_list:
+                cur_data = np.load(input_path)
+                assert cur_data.shape[0] >= 4096, "input pc_normal should have at least 4096 points"
+                idx = np.random.choice(cur_data.shape[0], 4096, replace=False)
+                cur_data = cur_data[idx]
+                self.data.append({'pc_normal': cur_data, 'uid': input_path.split('/')[-1].split('.')[0]})
+        elif input_type == 'mesh':
+            mesh_list = [load_mesh(p) for p in input_list]
+            if mc:
+                print("First Marching Cubes and then sample point cloud, need several minutes...")
+            pc_list, _ = process_mesh_to_pc(mesh_list, marching_cubes=mc)
+            for input_path, cur_data in zip(input_list, pc_list):
+                self.data.append({'pc_normal': cur_data, 'uid': input_path.split('/')[-1].split('.')[0]})
+        print(f"dataset total data samples: {len(self.data)}")
+
+    def __len__(self):
+        return len(self.data)
+
+    def __getitem__(self, idx):
+        from meshanything_b200.inputs import normalize_pc_normal
+        return {'pc_normal': normalize_pc_normal(self.data[idx]['pc_normal']), 'uid': self.data[idx]['uid']}
+
+
+def get_args():
+    parser = argparse.ArgumentParser("MeshAnything", add_help=False)
+    parser.add_argument('--llm', default="facebook/opt-350m", type=str)
+    parser.add_argument('--input_dir', default=None, type=str)
+    parser.add_argument('--input_path', default=None, type=str)
+    parser.add_argument('--out_dir', default="inference_out", type=str)
+    parser.add_argument('--pretrained_weights', default="MeshAnything_350m.pth", type=str)
+    parser.add_argument('--input_type', choices=['mesh', 'pc_normal'], default='pc',
+                        help="Type of the asset to process (default: pc)")
+    parser.add_argument("--codebook_size", default=8192, type=int)
+    parser.add_argument("--codebook_dim", default=1024, type=int)
+    parser.add_argument("--n_max_triangles", default=800, type=int)
+    parser.add_argument("--batchsize_per_gpu", default=1, type=int)
+    parser.add_argument("--seed", default=0, type=int)
+    parser.add_argument("--mc", default=False, action="store_true")
+    parser.add_argument("--sampling", default=False, action="store_true")
+    return parser.parse_args()
+
+
+def load_model(args, device=None):
+    model = MeshAnything(args)
+    print("load model over!!!")
+    if args.pretrained_weights == "synthetic":
+        from meshanything_b200 import checkpoint
+        tensors = checkpoint.synthetic_state_dict(0)
+    else:
+        from safetensors import safe_open
+        if not os.path.exists(args.pretrained_weights):
+            raise FileNotFoundError(f"{args.pretrained_weights}: put the published MeshAnything_350m.pth (safetensors) "
+                                    "here, or pass --pretrained_weights synthetic")
+        tensors = {}
+        with safe_open(args.pretrained_weights, framework="pt", device="cpu") as f:
+            for k in f.keys():
+                tensors[k] = f.get_tensor(k)
+    model.load_state_dict(tensors, strict=True, device=device)
+    print("load weights over!!!")
+    return model
+
+
+def export_obj(path, faces_xyz):
+    """merge_vertices + unique_faces + orange face colour of main.py:161-174 (trimesh when available)."""
+    vertices = faces_xyz.reshape(-1, 3)
+    triangles = np.arange(len(vertices)).reshape(-1, 3)
+    try:
+        import trimesh
+        mesh = trimesh.Trimesh(vertices=vertices, faces=triangles, force="mesh", merge_primitives=True)
+        mesh.merge_vertices()
+        mesh.update_faces(mesh.unique_faces())
+        mesh.fix_normals()
+        mesh.visual.face_colors = np.tile(np.array([255, 165, 0, 255], dtype=np.uint8), (len(mesh.faces), 1))
+        mesh.export(path)
+        return len(mesh.faces)
+    except ImportError:
+        uniq, inv = np.unique(np.round(vertices, 8), axis=0, return_inverse=True)
+        tri = inv.reshape(-1)[triangles]
+        _, keep = np.unique(np.sort(tri, axis=1), axis=0, return_index=True)
+        tri = tri[np.sort(keep)]
+        with open(path, "w") as f:
+            for v in uniq:
+                f.write(f"v {v[0]:.8f} {v[1]:.8f} {v[2]:.8f} 1.00000000 0.64705882 0.00000000\n")
+            for t in tri:
+                f.write(f"f {t[0] + 1} {t[1] + 1} {t[2] + 1}\n")
+        return len(tri)
+
+
+if __name__ == "__main__":
+    args = get_args()
+    from meshanything_b200 import parallel
+    rank, world, local = parallel.init_from_env()
+    cur_time = datetime.datetime.now().strftime("%d_%H-%M-%S")
+    checkpoint_dir = os.path.join(args.out_dir, cur_time)
+    os.makedirs(checkpoint_dir, exist_ok=True)
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    model = load_model(args, device)
+
+    if args.input_dir is not None:
+        input_list = sorted(os.listdir(args.input_dir))
+        if args.input_type == 'pc_normal':
+            input_list = [os.path.join(args.input_dir, x) for x in input_list if x.endswith('.npy')]
+        else:
+            input_list = [os.path.join(args.input_dir, x) for x in input_list
+                          if x.endswith('.ply') or x.endswith('.obj') or x.endswith('.npy')]
+    elif args.input_path is not None:
+        input_list = [args.input_path]
+    else:
+        raise ValueError("input_dir or input_path must be provided.")
+    np.random.seed(args.seed)
+    torch.manual_seed(args.seed)
+    dataset = Dataset(args.input_type, input_list, args.mc)
+
+    bs = args.batchsize_per_gpu
+    batches = [list(range(i, min(i + bs, len(dataset)))) for i in range(0, len(dataset), bs)]
+    begin_time = time.time()
+    print("Generation Start!!!")
+    for bi, idxs in enumerate(batches):
+        if bi % world != rank:
+            continue
+        items = [dataset[i] for i in idxs]
+        pc = torch.from_numpy(np.stack([it['pc_normal'] for it in items]))
+        outputs = model(pc, sampling=args.sampling)
+        for batch_id, it in enumerate(items):
+            recon_mesh = outputs[batch_id]
+            recon_mesh = recon_mesh[~torch.isnan(recon_mesh[:, 0, 0])]
+            save_path = os.path.join(checkpoint_dir, f'{it["uid"]}_gen.obj')
+            export_obj(save_path, recon_mesh.cpu().numpy())
+            print(f"{save_path} Over!!")
+    print(f"Total time: {time.time() - begin_time}")

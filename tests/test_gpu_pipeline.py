@@ -1,0 +1,118 @@
+"""-m gpu: encoder (a1-a8), detokenizer (a17-a18) and the MeshAnything.forward drop-in on the B200.
+
+Floating-point stages are compared with the fp32 torch restatement (oracle/torch_ref.py, itself pinned to the
+reference's own modules) under a stated tolerance: the GPU path rounds every Linear input/output to fp16 as CUDA
+autocast does in the reference, the restatement does not round.  Integer results (token ids) are bit-exact
+against the CPU oracle given the same prefix.
+"""
+import argparse
+
+import pytest
+import torch
+
+from meshanything_b200 import checkpoint as ck
+from meshanything_b200.inputs import synthetic_pc_normal
+
+gpu = pytest.mark.gpu
+
+# stated tolerances (measured margins in DESIGN.md section 6)
+TOL_PF_MAX, TOL_PF_MEAN = 6e-2, 6e-3          # point_feature: unit-variance LayerNorm output after 9 blocks
+TOL_PREFIX_MAX, TOL_PREFIX_MEAN = 1.2e-1, 1e-2  # prefix: std 1.4, after 16 more fp16-stream blocks + cond_proj
+F_SMALL = 8
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def full():
+    sd = ck.make_state_dict(ck.all_specs(24), 0)
+    return sd
+
+
+@gpu
+def test_encoder_vs_fp32_reference(full):
+    from meshanything_b200.encoder import EncoderArena
+    from oracle import torch_ref
+    pc = synthetic_pc_normal(3, first=0)
+    enc = EncoderArena(full, _dev())
+    pf, prefix = enc.forward(pc.to(_dev()))
+    with torch.no_grad():
+        rpf, rprefix = torch_ref.encoder_forward(full, pc)
+    d1, d2 = (pf.cpu() - rpf).abs(), (prefix.cpu() - rprefix).abs()
+    print("point_feature err max %.4g mean %.4g ; prefix err max %.4g mean %.4g" % (d1.max(), d1.mean(), d2.max(), d2.mean()))
+    assert d1.max() < TOL_PF_MAX and d1.mean() < TOL_PF_MEAN
+    assert d2.max() < TOL_PREFIX_MAX and d2.mean() < TOL_PREFIX_MEAN
+    # batch invariance of the canonical kernels: shape 1 alone gives the same bits
+    pf1, prefix1 = enc.forward(pc[1:2].to(_dev()))
+    assert torch.equal(pf1[0], pf[1]) and torch.equal(prefix1[0], prefix[1])
+
+
+@gpu
+def test_detokenizer_vs_fp32_reference(full):
+    from meshanything_b200.encoder import EncoderArena, TokenizerArena
+    from oracle import torch_ref
+    F = 12
+    g = torch.Generator().manual_seed(5)
+    gen_ids = torch.randint(3, 8195, (2, 9 * F + 2), generator=g, dtype=torch.int64)
+    gen_ids[0, 1 + 9 * 7 + 4] = 1          # eos inside face 7 -> face 7 absent
+    gen_ids[0, 1 + 9 * 10:] = 2            # padding after face 9
+    gen_ids[1, 1 + 9 * 11 + 8] = 0
+    pc = synthetic_pc_normal(2, first=0)
+    pf, _ = EncoderArena(full, _dev()).forward(pc.to(_dev()))
+    tok = TokenizerArena(full, _dev())
+    coords, ids = tok.detokenize(gen_ids.to(torch.int32).to(_dev()), pf, F, want_ids=True)
+    ref_ids = torch_ref.postprocess_ids(gen_ids, F)
+    assert torch.equal(ids.cpu().long(), ref_ids)
+    with torch.no_grad():
+        rcoords, rlogits = torch_ref.detokenize(full, ref_ids, pf.cpu(), return_logits=True)
+    c = coords.cpu()
+    assert torch.equal(torch.isnan(c), torch.isnan(rcoords))
+    valid = ~torch.isnan(rcoords)
+    same = (c[valid] == rcoords[valid])
+    # a bin may differ only where the reference's top-2 logit margin is within the fp16 noise of the logits
+    top2 = torch.topk(rlogits, 2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1]).view(2, F, 3, 3)[valid]
+    print("detok bins equal: %d / %d ; max margin at a mismatch %.4g" % (same.sum(), same.numel(),
+                                                                         margin[~same].max() if (~same).any() else 0.0))
+    assert same.float().mean() > 0.97
+    assert (margin[~same] < 0.08).all()
+    assert ((c[valid] - rcoords[valid]).abs() <= 1.0 / 128 + 1e-6)[~same].float().mean() > 0.5 or same.all()
+
+
+@gpu
+def test_forward_drop_in(full):
+    """MeshAnything(args).load_state_dict(strict=True); model(pc_normal) -> [B,F,3,3]; ids bit-exact vs the oracle."""
+    from MeshAnything.models.meshanything import MeshAnything
+    from oracle.decoder import OracleDecoder
+    from oracle import torch_ref
+    args = argparse.Namespace(llm="facebook/opt-350m", codebook_size=8192, codebook_dim=1024, n_max_triangles=F_SMALL,
+                              seed=0)
+    model = MeshAnything(args)
+    with pytest.raises(RuntimeError):
+        model.load_state_dict({k: v for k, v in full.items() if k != "cond_proj.bias"}, strict=True, device=_dev())
+    model.load_state_dict(full, strict=True, device=_dev())
+    pc = synthetic_pc_normal(2, first=3)                       # host tensor: forward copies it
+    out = model(pc)
+    assert out.shape == (2, F_SMALL, 3, 3) and out.dtype == torch.float32 and out.is_cuda
+    v = out[~torch.isnan(out)]
+    assert (v >= -0.5).all() and (v < 0.5).all()
+    ids = model.last_ids.cpu()
+    # decoder leg: same prefix -> the oracle's ids
+    pf, prefix = model.point_encoder._last
+    oracle = OracleDecoder(full, 24, 257 + 9 * F_SMALL + 2)
+    for b in range(2):
+        ref, _ = oracle.generate(prefix[b].cpu(), 9 * F_SMALL + 2)
+        assert ids[b].tolist()[:len(ref)] == ref
+    # detokenizer leg on the same ids
+    with torch.no_grad():
+        rc = torch_ref.detokenize(full, torch_ref.postprocess_ids(ids.long(), F_SMALL), pf.cpu())
+    assert torch.equal(torch.isnan(out.cpu()), torch.isnan(rc))
+    valid = ~torch.isnan(rc)
+    assert (out.cpu()[valid] == rc[valid]).float().mean() > 0.9
+    # one shape alone, and sampling mode
+    out1 = model(pc[:1].to(_dev()))
+    assert torch.equal(torch.nan_to_num(out1[0]), torch.nan_to_num(out[0]))
+    outs = model(pc, sampling=True)
+    assert outs.shape == out.shape
