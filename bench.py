@@ -167,23 +167,35 @@ def main():
     from meshanything_b200 import capi
     from meshanything_b200.decoder import DecoderArena, Generator
 
-    sd_host = make_state_dict(specs, 0) if rank == 0 else None
-    sd = parallel.broadcast_state_dict(sd_host, specs, dev)      # one NCCL broadcast, no collective in the step
-    arena = DecoderArena(sd, dev, n_layers=NL)
+    import argparse as _ap
+    from meshanything_b200.checkpoint import all_specs
+    from meshanything_b200.inputs import synthetic_pc_normal
+    from MeshAnything.models.meshanything import MeshAnything
+    full_specs = all_specs(NL)
+    sd_host = make_state_dict(full_specs, 0) if rank == 0 else None
+    sd = parallel.broadcast_state_dict(sd_host, full_specs, dev)  # ONE NCCL broadcast; no collective in the step
+    del sd_host
+    margs = _ap.Namespace(llm="facebook/opt-350m", codebook_size=8192, codebook_dim=1024, n_max_triangles=F, seed=0)
+    model = MeshAnything(margs)
+    if NL != 24:
+        model.expected_keys = lambda: list(full_specs.keys())
+    model.load_state_dict(sd, strict=True, device=dev)
+    arena = model._dec
     del sd
+    torch.cuda.empty_cache()
     tmax = 257 + max_new
-    gen = Generator(arena, B, tmax)
+    gen = model._generator(B)
     flags = args.flags | capi.GEN_NO_EARLY_EXIT
-    prefix_host = synthetic_prefix(B, rank * B).pin_memory()
-    prefix_dev = prefix_host.to(dev)
+    pc_host = synthetic_pc_normal(B, first=rank * B).pin_memory()     # fp16 [B,4096,6]
+    pc_dev = pc_host.to(dev)
+    _, prefix_dev = model.point_encoder.encode_with_prefix(pc_dev)
+    prefix_dev = prefix_dev.clone()
 
-    def one_step_resident():
-        return gen.generate(prefix_dev, max_new, do_sample=args.sampling, seed=0, flags=flags)
+    def one_step_resident():                                          # the whole hot path, inputs resident in HBM
+        return model(pc_dev, sampling=args.sampling)
 
-    def one_step_e2e():
-        p = prefix_host.to(dev, non_blocking=True)
-        ids, lens = gen.generate(p, max_new, do_sample=args.sampling, seed=0, flags=flags)
-        return ids.to("cpu", non_blocking=False), lens
+    def one_step_e2e():                                               # public API, host buffers in and out
+        return model(pc_host, sampling=args.sampling).to("cpu")
 
     def barrier():
         if world > 1:
@@ -214,10 +226,16 @@ def main():
     clocks = sampler.stop()
     launches = capi.lib().ma_launch_count() - launches0
     ms_e2e, out_e2e = timed(one_step_e2e, args.steps)
+    # stage split of one pass (encoder / decode loop / detokenizer), device timed
+    ms_enc, _ = timed(lambda: model.point_encoder.encode_with_prefix(pc_dev), args.steps)
+    ms_gen, gen_out = timed(lambda: gen.generate(prefix_dev, max_new, do_sample=args.sampling, seed=0, flags=flags),
+                            args.steps)
+    ms_all = ms
 
-    ids = out[0]
+    ids = gen_out[0]
+    ms = ms_gen   # the roofline below is about the decode loop
     n_tokens = world * B * face_tokens_per_seq * args.steps
-    value = n_tokens / (ms / 1000.0)
+    value = n_tokens / (ms_all / 1000.0)
     e2e_value = n_tokens / (ms_e2e / 1000.0)
 
     # ---- roofline of the decode step (the HBM-bound part): algorithmic bytes per token-step / time per step
@@ -241,12 +259,15 @@ def main():
     dec_ms = ms / args.steps - max(0.0, t_prefill_ms)             # decode-loop part of one generate
     achieved = alg_bytes_per_gen / (dec_ms / 1000.0) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "decode step = 97 fast_gemv_kernel + 24 attention_kernel launches (one CUDA graph)"
-        if B == 1 else "decode step (gemm_canon + attention kernels, one CUDA graph)",
+        "bound": "hbm",
+        "kernel": ("decode_mega_kernel (persistent: all 121 phases of a token, 512 tokens per launch)"
+                   if (B == 1 and not args.sampling and not (flags & capi.GEN_NO_MEGA)) else
+                   "decode step = 97 fast_gemv_kernel + 24 attention_kernel launches (one CUDA graph)" if B == 1 else
+                   "decode step (gemm_canon + attention kernels, one CUDA graph)"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": None,
         "algorithmic_bytes_per_launch": alg_bytes_per_gen / n_dec,
-        "launch": "one decode step (graph launch); bytes = fp16 weights %d + KV read/write averaged over the run" % wbytes,
+        "launch": "one decode step (one token of every sequence); bytes = fp16 weights %d + KV read/write averaged over the run" % wbytes,
         "us_per_step_avg": dec_ms * 1000.0 / n_dec,
         "short_context": {"us_per_step": us_step_short, "bytes_per_step": short_bytes,
                           "achieved": short_bytes / us_step_short / 1e3, "frac": short_bytes / us_step_short / 1e3 / peak,
@@ -260,16 +281,19 @@ def main():
             cpu = cpu_oracle_tokens_per_s(make_state_dict(specs, 0), NL)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 weights/activations, f32 accumulate", "data": "synthetic",
             "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world} (batch sharded, "
-                       "weights broadcast once over NCCL)", "inputs": "prefix resident in HBM",
+                       "weights broadcast once over NCCL)",
+                       "inputs": "pc_normal fp16 [B,4096,6] resident in HBM; one step = encoder + generate + detokenize",
+                       "stage_ms": {"encoder": ms_enc / args.steps, "generate": ms_gen / args.steps,
+                                    "detokenize_and_rest": (ms_all - ms_enc - ms_gen) / args.steps},
                        "l2": "inputs larger than L2: 623.5 MB of weights + KV streamed per token (L2 = 126 MB)",
                        "checkpoint": "synthetic seed 0 (random weights: no early EOS, every sequence runs the cap)"},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(prefix_host.numel() * 4),
-                    "d2h_bytes_per_step": int(out_e2e[0].numel() * 4),
-                    "api": "meshanything_b200.decoder.Generator.generate (decoder leg of MeshAnything.forward)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pc_host.numel() * 2),
+                    "d2h_bytes_per_step": int(out_e2e.numel() * 4),
+                    "api": "MeshAnything.models.meshanything.MeshAnything.forward(pc_normal on the host) -> .cpu()"},
             "gpu_launches": int(launches), "clocks": clocks,
             "check": {"first_ids": ids[0, :8].cpu().tolist()},
         }

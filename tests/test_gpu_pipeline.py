@@ -16,8 +16,8 @@ from meshanything_b200.inputs import synthetic_pc_normal
 gpu = pytest.mark.gpu
 
 # stated tolerances (measured margins in DESIGN.md section 6)
-TOL_PF_MAX, TOL_PF_MEAN = 6e-2, 6e-3          # point_feature: unit-variance LayerNorm output after 9 blocks
-TOL_PREFIX_MAX, TOL_PREFIX_MEAN = 1.2e-1, 1e-2  # prefix: std 1.4, after 16 more fp16-stream blocks + cond_proj
+TOL_PF_MAX, TOL_PF_MEAN = 1.5e-2, 2.5e-3      # measured 3.5e-3 / 5.9e-4 (unit-variance LayerNorm output after 9 blocks)
+TOL_PREFIX_MAX, TOL_PREFIX_MEAN = 4e-2, 6e-3  # measured 1.0e-2 / 1.6e-3 (std 1.4, 16 more fp16-stream blocks + cond_proj)
 F_SMALL = 8
 
 
