@@ -42,6 +42,8 @@ class DecoderArena:
 
         def f32(t):
             t = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            if t.data_ptr() % 256:      # a view into a packed buffer (e.g. the broadcast arena): kernels use 16-byte loads
+                t = t.clone()
             self.keep.append(t)
             return t
 

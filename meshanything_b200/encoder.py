@@ -64,6 +64,8 @@ class _Arena:
 
     def f32(self, t: torch.Tensor) -> int:
         t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        if t.data_ptr() % 256:          # a view into a packed buffer: kernels use 16-byte loads
+            t = t.clone()
         self.keep.append(t)
         return t.data_ptr()
 

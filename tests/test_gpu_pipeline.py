@@ -92,7 +92,12 @@ def test_forward_drop_in(full):
     model = MeshAnything(args)
     with pytest.raises(RuntimeError):
         model.load_state_dict({k: v for k, v in full.items() if k != "cond_proj.bias"}, strict=True, device=_dev())
-    model.load_state_dict(full, strict=True, device=_dev())
+    # weights arrive as views into ONE packed fp32 device buffer (what the NCCL broadcast at init produces):
+    # arbitrary 4-byte offsets must not break the 16-byte loads of the kernels
+    from meshanything_b200 import parallel
+    packed = parallel.broadcast_state_dict(full, ck.all_specs(24), _dev())
+    model.load_state_dict(packed, strict=True, device=_dev())
+    del packed
     pc = synthetic_pc_normal(2, first=3)                       # host tensor: forward copies it
     out = model(pc)
     assert out.shape == (2, F_SMALL, 3, 3) and out.dtype == torch.float32 and out.is_cuda
