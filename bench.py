@@ -252,10 +252,11 @@ def main():
             g2.generate(prefix_dev, nn, flags=flags)
         t, _ = timed(lambda: g2.generate(prefix_dev, nn, flags=flags), 3)
         return t / 3
-    t100, t300 = short(100), short(300)
-    us_step_short = (t300 - t100) / 200.0 * 1000.0
-    short_bytes = wbytes + KV_BYTES_PER_POS * B * (257 + 200 + 1)
-    t_prefill_ms = t100 - 99 * us_step_short / 1000.0
+    n_lo, n_hi = (100, 300) if max_new >= 300 else (max(2, max_new // 4), max_new)
+    t100, t300 = short(n_lo), short(n_hi)
+    us_step_short = (t300 - t100) / float(n_hi - n_lo) * 1000.0
+    short_bytes = wbytes + KV_BYTES_PER_POS * B * (257 + (n_lo + n_hi) // 2 + 1)
+    t_prefill_ms = t100 - (n_lo - 1) * us_step_short / 1000.0
     dec_ms = ms / args.steps - max(0.0, t_prefill_ms)             # decode-loop part of one generate
     achieved = alg_bytes_per_gen / (dec_ms / 1000.0) / 1e9
     roofline = {
@@ -271,7 +272,7 @@ def main():
         "us_per_step_avg": dec_ms * 1000.0 / n_dec,
         "short_context": {"us_per_step": us_step_short, "bytes_per_step": short_bytes,
                           "achieved": short_bytes / us_step_short / 1e3, "frac": short_bytes / us_step_short / 1e3 / peak,
-                          "note": "steps at context ~357..557 (GEMV-dominated): (T(300)-T(100))/200"},
+                          "note": "steps at context ~%d..%d (GEMV-dominated): (T(%d)-T(%d))/%d" % (257 + n_lo, 257 + n_hi, n_hi, n_lo, n_hi - n_lo)},
         "prefill_ms": t_prefill_ms,
     }
 

@@ -347,7 +347,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
 int ma_decoder_debug(void* ws_, int B, int tmax, int what, void* host_out, int nbytes) {
   DecWs ws = carve(ws_, B, tmax, 8195 + 61);
   cudaDeviceSynchronize();
-  const char* src = (const char*)ws.mega + (what == 0 ? mega_error_flag_offset() : mega_trace_offset());
+  const char* src = (const char*)ws.mega + (what == 0 ? mega_error_flag_offset() : what == 1 ? mega_trace_offset() : mega_trace_cta_offset());
   return cudaMemcpy(host_out, src, (size_t)nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 

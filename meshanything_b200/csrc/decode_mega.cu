@@ -21,8 +21,9 @@
 
 namespace ma {
 
-constexpr int MG_THREADS = 256;
-constexpr int MG_WARPS = 8;
+constexpr int MG_THREADS = 512;  // 16 warps: one or two weight rows per warp in every GEMV phase, two attention teams
+constexpr int MG_WARPS = 16;
+constexpr int TEAM = 256;        // threads of one attention team (8 warps = 32 group-lanes, the canonical structure)
 constexpr int PARTF = 66;      // o[64], max, sum
 constexpr int MAX_CHUNKS = 72;  // 18432 keys
 
@@ -36,6 +37,7 @@ struct MegaWs {
   int error;              // 1: a poll timed out
   int pad_[3];
   unsigned long long trace[1280];
+  unsigned long long trace_cta[160 * 8];   // per-CTA stamps of one (step, layer): skew analysis
   ma_decoder_weights w;   // device copy of the weight table
   alignas(256) uint2 part_w[NHEAD * MAX_CHUNKS * PARTF];  // {fp32 bits, epoch}
   alignas(256) __half bias_cta[MA_MAX_LAYERS * 160 * 128];  // [layer][cta][128]: this CTA's biases (see BIAS_*)
@@ -99,11 +101,47 @@ __device__ __forceinline__ uint32_t ll_wait1(const uint2* p, uint32_t ep, int* e
   }
   return v.x;
 }
-// gather a flagged fp16 vector of `nhalf` elements into shared memory (4 halfs per thread and round)
+// wait for N consecutive 16-byte units (2 words each) starting at p with stride `stride` units: all loads are
+// issued before any flag is checked, and only the units that are not there yet are polled again
+template <int N>
+__device__ __forceinline__ void ll_wait_units(const uint2* p, int stride, uint32_t ep, uint2* out, int* err) {
+  uint4 v[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) v[i] = ll_load2(p + 2 * i * stride);
+  unsigned spins = 0;
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      if (v[i].y != ep || v[i].w != ep) {
+        ok = false;
+        v[i] = ll_load2(p + 2 * i * stride);
+      }
+    }
+    if (ok) break;
+    if (++spins > SPIN_LIMIT) { *err = 1; break; }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) out[i] = make_uint2(v[i].x, v[i].z);
+}
+// gather a flagged fp16 vector of `nhalf` elements (1024 or 4096) into shared memory
+__device__ __forceinline__ void store_x4(float* dst, uint2 d) {  // 4 fp16 -> 4 fp32 (exact)
+  const __half2* hh = reinterpret_cast<const __half2*>(&d);
+  const float2 p0 = __half22float2(hh[0]), p1 = __half22float2(hh[1]);
+  *reinterpret_cast<float4*>(dst) = make_float4(p0.x, p0.y, p1.x, p1.y);
+}
 __device__ __forceinline__ void ll_gather(const uint2* src, int nhalf, uint32_t ep, __half* dst, int* err) {
-  for (int u = threadIdx.x; u < nhalf / 4; u += MG_THREADS) {
-    const uint2 d = ll_wait2(src + 2 * u, ep, err);
-    *reinterpret_cast<uint2*>(dst + 4 * u) = d;
+  const int tid = threadIdx.x;
+  if (nhalf == FFN) {  // 1024 units: two per thread, both in flight
+    uint2 d[2];
+    ll_wait_units<2>(src + 2 * tid, MG_THREADS, ep, d, err);
+    *reinterpret_cast<uint2*>(dst + 4 * tid) = d[0];
+    *reinterpret_cast<uint2*>(dst + 4 * (tid + MG_THREADS)) = d[1];
+  } else {
+    for (int u = tid; u < nhalf / 4; u += MG_THREADS) {
+      const uint2 d = ll_wait2(src + 2 * u, ep, err);
+      *reinterpret_cast<uint2*>(dst + 4 * u) = d;
+    }
   }
 }
 
@@ -117,68 +155,124 @@ struct alignas(128) MegaSmem {
   alignas(16) __half bias[2][128];
   ma_decoder_weights wtab;          // pointer table (kept on chip: every access would be an HBM miss)
   float red[8];
-  float wmax[8];
-  float ared[8][65];
-  float bval[8];
-  int bidx[8];
+  float wmax[2][8];
+  float ared[2][8][65];
+  float bval[MG_WARPS];
+  int bidx[MG_WARPS];
+  float cstage[2 * 2 * MAX_CHUNKS];  // per team: {max, sum} of the chunks of one head during the merge
+  alignas(16) __half stage16[64];    // fp16 results of this CTA's rows of the current GEMV phase
   alignas(16) float hres[HID];  // residual stream
-  alignas(16) __half xs[FFN];   // fp16 input vector of the current GEMV
+  alignas(16) __half xs[FFN];   // fp16 input vector of the current GEMV (fp32 would double the shared-memory
+                                // traffic, which bounds the GEMV phases: every warp re-reads x)
 };
 
 __device__ __forceinline__ uint4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Rows of this CTA held in shared memory `sw` ([nrows][K], nrows even): pair p = rows (2p, 2p+1); warp w owns
-// pairs w, w+8, w+16, w+24 and runs two pairs (4 rows) at a time for instruction-level parallelism.  The four
-// warp sums are produced by a partially transposing butterfly (same additions as warp_sum, 6 shuffles for 4
-// values).  `emit(n_even, h0, h1)` is called by one lane with the fp16 results of rows n_even, n_even+1.
-template <int K, typename Emit>
-__device__ __forceinline__ void gemv_pairs(const __half* sw, int nrows, int row0, const __half* bias, const __half* xs,
-                                           int warp, int lane, Emit emit) {
+// LayerNorm of 1024 values by the first 256 threads (thread t owns 4t..4t+3: the canonical block sum); the other
+// threads only take part in the barriers.  Returns the normalised values in v (threads < 256).
+__device__ __forceinline__ void layernorm_1024(float* v, const float* gamma, const float* beta, float* red, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool act = tid < 256;
+  const float inv = __fdiv_rn(1.0f, 1024.0f);
+  float p = act ? fadd(fadd(v[0], v[1]), fadd(v[2], v[3])) : 0.0f;
+  p = warp_sum(p);
+  __syncthreads();
+  if (act && lane == 0) red[warp] = p;
+  __syncthreads();
+  const float mean = fmul(warp_tree(red, 8), inv);
+  const float d0 = fsub(v[0], mean), d1 = fsub(v[1], mean), d2 = fsub(v[2], mean), d3 = fsub(v[3], mean);
+  float q = act ? fadd(fadd(fmul(d0, d0), fmul(d1, d1)), fadd(fmul(d2, d2), fmul(d3, d3))) : 0.0f;
+  q = warp_sum(q);
+  __syncthreads();
+  if (act && lane == 0) red[warp] = q;
+  __syncthreads();
+  const float var = fmul(warp_tree(red, 8), inv);
+  const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(fadd(var, MA_LN_EPS)));
+  if (act) {
+    const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * tid);
+    const float4 b = *reinterpret_cast<const float4*>(beta + 4 * tid);
+    v[0] = ffma(fmul(d0, rstd), g.x, b.x);
+    v[1] = ffma(fmul(d1, rstd), g.y, b.y);
+    v[2] = ffma(fmul(d2, rstd), g.z, b.z);
+    v[3] = ffma(fmul(d3, rstd), g.w, b.w);
+  }
+}
+
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TEAM) : "memory"); }
+
+// Rows of this CTA held in shared memory `sw` ([nrows][K]): warp w computes rows w, w+16, w+32, w+48 (those
+// that exist) together; lane 0 writes fp16(dot + bias) (ReLU optional) to stage[row].  The caller synchronises and
+// emits the rows pairwise.  `bias` is this CTA's slice (shared memory) or null.
+__device__ __forceinline__ void load_x8(const float* p, float* xf) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  xf[0] = a.x; xf[1] = a.y; xf[2] = a.z; xf[3] = a.w; xf[4] = b.x; xf[5] = b.y; xf[6] = b.z; xf[7] = b.w;
+}
+
+template <int K, bool RELU>
+__device__ __forceinline__ void gemv_stage(const __half* sw, int nrows, const __half* bias, const __half* xs, int warp,
+                                           int lane, __half* stage) {
   constexpr int G = K / 256;
-  const int npairs = nrows >> 1;
+  if (warp >= nrows) return;
+  const __half* w[4];
+  bool has[4];
 #pragma unroll
-  for (int i = 0; i < 4; i += 2) {
-    const int pA = warp + MG_WARPS * i, pB = pA + MG_WARPS;
-    if (pA >= npairs) break;
-    const bool hasB = pB < npairs;
-    const __half* wA = sw + (size_t)(2 * pA) * K + 8 * lane;
-    const __half* wB = sw + (size_t)(2 * (hasB ? pB : pA)) * K + 8 * lane;
-    float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int i = 0; i < 4; i++) {
+    const int r = warp + MG_WARPS * i;
+    has[i] = r < nrows;
+    w[i] = sw + (size_t)(has[i] ? r : warp) * K + 8 * lane;
+  }
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  if (!has[1]) {  // one row (out_proj, fc2, the tail warps of qkv / fc1)
 #pragma unroll 4
+    for (int g = 0; g < G; g++) {
+      float xf[8], f[8];
+      unpack8(*reinterpret_cast<const uint4*>(xs + 256 * g + 8 * lane), xf);
+      unpack8(*reinterpret_cast<const uint4*>(w[0] + 256 * g), f);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[0] = ffma(f[j], xf[j], acc[0]);
+    }
+  } else if (!has[2]) {  // two rows (qkv, fc1)
+#pragma unroll 4
+    for (int g = 0; g < G; g++) {
+      float xf[8], f0[8], f1[8];
+      unpack8(*reinterpret_cast<const uint4*>(xs + 256 * g + 8 * lane), xf);
+      unpack8(*reinterpret_cast<const uint4*>(w[0] + 256 * g), f0);
+      unpack8(*reinterpret_cast<const uint4*>(w[1] + 256 * g), f1);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        acc[0] = ffma(f0[j], xf[j], acc[0]);
+        acc[1] = ffma(f1[j], xf[j], acc[1]);
+      }
+    }
+  } else {  // three or four rows (lm_head)
+#pragma unroll 2
     for (int g = 0; g < G; g++) {
       float xf[8], f[4][8];
       unpack8(*reinterpret_cast<const uint4*>(xs + 256 * g + 8 * lane), xf);
-      unpack8(*reinterpret_cast<const uint4*>(wA + 256 * g), f[0]);
-      unpack8(*reinterpret_cast<const uint4*>(wA + K + 256 * g), f[1]);
-      unpack8(*reinterpret_cast<const uint4*>(wB + 256 * g), f[2]);
-      unpack8(*reinterpret_cast<const uint4*>(wB + K + 256 * g), f[3]);
+#pragma unroll
+      for (int i = 0; i < 4; i++) unpack8(*reinterpret_cast<const uint4*>(w[i] + 256 * g), f[i]);
 #pragma unroll
       for (int j = 0; j < 8; j++) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) acc[r] = ffma(f[r][j], xf[j], acc[r]);
+        for (int i = 0; i < 4; i++) acc[i] = ffma(f[i][j], xf[j], acc[i]);
       }
     }
-    // xor-16: lanes with bit 4 clear keep rows 0,1 (pair A), the others rows 2,3 (pair B)
-    const bool up16 = (lane & 16) != 0;
-    float k0 = up16 ? acc[2] : acc[0], k1 = up16 ? acc[3] : acc[1];
-    float s0 = up16 ? acc[0] : acc[2], s1 = up16 ? acc[1] : acc[3];
-    k0 = fadd(k0, __shfl_xor_sync(0xffffffffu, s0, 16));
-    k1 = fadd(k1, __shfl_xor_sync(0xffffffffu, s1, 16));
-    // xor-8: lanes with bit 3 clear keep the first row of their pair
-    const bool up8 = (lane & 8) != 0;
-    float k = up8 ? k1 : k0, sx = up8 ? k0 : k1;
-    k = fadd(k, __shfl_xor_sync(0xffffffffu, sx, 8));
-    k = fadd(k, __shfl_xor_sync(0xffffffffu, k, 4));
-    k = fadd(k, __shfl_xor_sync(0xffffffffu, k, 2));
-    k = fadd(k, __shfl_xor_sync(0xffffffffu, k, 1));
-    // lane 0: row 2pA, lane 8: row 2pA+1, lane 16: row 2pB, lane 24: row 2pB+1
-    const int myrow = 2 * (up16 ? pB : pA) + (up8 ? 1 : 0);
-    const float bf = bias ? __half2float(bias[min(myrow, nrows - 1)]) : 0.0f;
-    const __half hv = __float2half_rn(fadd(k, bf));
-    const __half hn = __shfl_down_sync(0xffffffffu, hv, 8);
-    if (lane == 0) emit(row0 + 2 * pA, hv, hn);
-    if (lane == 16 && hasB) emit(row0 + 2 * pB, hv, hn);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (i == 0 || has[1]) acc[i] = warp_sum(acc[i]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (has[i]) {
+        const int r = warp + MG_WARPS * i;
+        __half h = __float2half_rn(fadd(acc[i], bias ? __half2float(bias[r]) : 0.0f));
+        if (RELU && __half2float(h) < 0.0f) h = __float2half_rn(0.0f);
+        stage[r] = h;
+      }
+    }
   }
 }
 
@@ -218,7 +312,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
   __half* bufC = bufD + (size_t)a.rows_qkv * HID;                         // out_proj rows
   __half* bufA = bufC + (size_t)a.rows_out * HID;                         // fc1 rows
   __half* bufB = bufA + (size_t)a.rows_fc1 * HID;                         // fc2 rows (K = 4096)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3, li = lane & 7;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int team = warp >> 3, wt = warp & 7, tl = tid & (TEAM - 1);       // attention team / warp and thread in it
+  const int grp = lane >> 3, li = lane & 7;
   MegaWs* ws = a.ws;
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&ws->w);
@@ -263,6 +359,32 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
   unsigned long long* tr = (a.trace && cta == 0 && tid == 0) ? ws->trace : nullptr;
   int tri = 0;
 #define STAMP() do { if (tr && tri < 1270) tr[tri++] = gtimer(); } while (0)
+  // every CTA stamps phase k of (second traced step, layer NL/2)
+#define CSTAMP(k) do { if (a.trace && tid == 0 && step == 1 && L == NL / 2) ws->trace_cta[cta * 8 + (k)] = gtimer(); } while (0)
+
+  // xs <- fp16(v) and hres <- v for the 1024-wide vector owned 4 per thread by the first 256 threads
+  auto publish_x = [&](const float* v, bool keep_hres) {
+    if (tid < 256) {
+      if (keep_hres) *reinterpret_cast<float4*>(sm.hres + 4 * tid) = make_float4(v[0], v[1], v[2], v[3]);
+      __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(sm.xs + 4 * tid) = u;
+    }
+  };
+  // v <- hres + float(flagged vector words of this thread)
+  auto residual_in = [&](const uint2* words, uint32_t ep, float* v) {
+    if (tid < 256) {
+      const float4 hv = *reinterpret_cast<const float4*>(sm.hres + 4 * tid);
+      const uint2 d = ll_wait2(words + 2 * tid, ep, err);
+      const __half2* hh = reinterpret_cast<const __half2*>(&d);
+      const float2 p0 = __half22float2(hh[0]), p1 = __half22float2(hh[1]);
+      v[0] = fadd(hv.x, p0.x); v[1] = fadd(hv.y, p0.y); v[2] = fadd(hv.z, p1.x); v[3] = fadd(hv.w, p1.y);
+    } else {
+      v[0] = v[1] = v[2] = v[3] = 0.0f;
+    }
+  };
 
   for (int step = 0; step < a.n_steps; step++) {
     if (gen >= a.max_new || fin) break;  // uniform across the grid
@@ -279,15 +401,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
       __half* kc = a.kv + ((size_t)(L * 2 + 0)) * NHEAD * T * HD;
       __half* vc = a.kv + ((size_t)(L * 2 + 1)) * NHEAD * T * HD;
 
-      // ---------------- K/V prefetch into registers: first attention item of this CTA (rows < pos are old)
+      // ---------------- K/V prefetch into registers: first attention item of this team (rows < pos are old)
       uint4 kreg[8], vreg[8];
-      int item = cta;
+      // attention items are dealt from the LAST CTA downwards (those CTAs own no out_proj / fc2 / qkv rows), first to
+      // the teams 0 of all CTAs, then to the teams 1
+      int item = team * ncta + (ncta - 1 - cta);
       if (item < nitems) {
         const int c = item >> 4, h = item & 15;
         const long base = ((long)h * T + (long)c * MA_ATTN_CHUNK) * HD;
 #pragma unroll
         for (int rho = 0; rho < 8; rho++) {
-          const int r = 32 * rho + 4 * warp + grp;
+          const int r = 32 * rho + 4 * wt + grp;
           if (c * MA_ATTN_CHUNK + r < pos) {
             kreg[rho] = ldcg16(kc + base + (long)r * HD + 8 * li);
             vreg[rho] = ldcg16(vc + base + (long)r * HD + 8 * li);
@@ -297,80 +421,81 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
 
       // ---------------- qkv phase: input = token embedding (layer 0) or LN2(hres + fc2 output) of the previous layer
       {
-        float v[4];
+        float v[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (L == 0) {
-          float4 X;
-          int fidx;
-          if (tok < 3) {
-            X = *reinterpret_cast<const float4*>(W.extra + (long)tok * HID + 4 * tid);
-            fidx = tok;
-          } else {
-            const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(W.tok_table) +
-                                                            (long)(tok - 3) * HID + 4 * tid);
-            const __half2* hh = reinterpret_cast<const __half2*>(&u);
-            const float2 p0 = __half22float2(hh[0]), p1 = __half22float2(hh[1]);
-            X = make_float4(p0.x, p0.y, p1.x, p1.y);
-            int r = (gen - 2) % 9;
-            if (r < 0) r += 9;
-            fidx = r + 3;
+          if (tid < 256) {
+            float4 X;
+            int fidx;
+            if (tok < 3) {
+              X = *reinterpret_cast<const float4*>(W.extra + (long)tok * HID + 4 * tid);
+              fidx = tok;
+            } else {
+              const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(W.tok_table) +
+                                                              (long)(tok - 3) * HID + 4 * tid);
+              const __half2* hh = reinterpret_cast<const __half2*>(&u);
+              const float2 p0 = __half22float2(hh[0]), p1 = __half22float2(hh[1]);
+              X = make_float4(p0.x, p0.y, p1.x, p1.y);
+              int r = (gen - 2) % 9;
+              if (r < 0) r += 9;
+              fidx = r + 3;
+            }
+            const float4 F = *reinterpret_cast<const float4*>(W.tok_pos + (long)fidx * HID + 4 * tid);
+            const float4 C = *reinterpret_cast<const float4*>(W.cond + HID + 4 * tid);
+            const float4 P = *reinterpret_cast<const float4*>(W.pos + (long)(pos + 2) * HID + 4 * tid);
+            v[0] = fadd(fadd(fadd(X.x, F.x), C.x), P.x);
+            v[1] = fadd(fadd(fadd(X.y, F.y), C.y), P.y);
+            v[2] = fadd(fadd(fadd(X.z, F.z), C.z), P.z);
+            v[3] = fadd(fadd(fadd(X.w, F.w), C.w), P.w);
           }
-          const float4 F = *reinterpret_cast<const float4*>(W.tok_pos + (long)fidx * HID + 4 * tid);
-          const float4 C = *reinterpret_cast<const float4*>(W.cond + HID + 4 * tid);
-          const float4 P = *reinterpret_cast<const float4*>(W.pos + (long)(pos + 2) * HID + 4 * tid);
-          v[0] = fadd(fadd(fadd(X.x, F.x), C.x), P.x);
-          v[1] = fadd(fadd(fadd(X.y, F.y), C.y), P.y);
-          v[2] = fadd(fadd(fadd(X.z, F.z), C.z), P.z);
-          v[3] = fadd(fadd(fadd(X.w, F.w), C.w), P.w);
         } else {
-          const float4 hv = *reinterpret_cast<const float4*>(sm.hres + 4 * tid);
-          const uint2 d = ll_wait2(ws->yb_w + 2 * tid, ep - 1, err);  // fc2 output of layer L-1
-          const __half2* hh = reinterpret_cast<const __half2*>(&d);
-          const float2 p0 = __half22float2(hh[0]), p1 = __half22float2(hh[1]);
-          v[0] = fadd(hv.x, p0.x); v[1] = fadd(hv.y, p0.y); v[2] = fadd(hv.z, p1.x); v[3] = fadd(hv.w, p1.y);
+          residual_in(ws->yb_w, ep - 1, v);  // fc2 output of layer L-1
           mbar_wait(&sm.lnbar[1], parL2);
           parL2 ^= 1;
-          layernorm4(v, sm.ln2, sm.ln2 + HID, MA_LN_EPS, HID, sm.red);
+          layernorm_1024(v, sm.ln2, sm.ln2 + HID, sm.red, tid);
           __syncthreads();  // every thread has read its gamma/beta
           if (tid == 0) fill_ln(sm.ln2, W.ln2g[L], W.ln2b[L], &sm.lnbar[1]);
         }
-        *reinterpret_cast<float4*>(sm.hres + 4 * tid) = make_float4(v[0], v[1], v[2], v[3]);
-        __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-        uint2 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(sm.xs + 4 * tid) = u;
+        publish_x(v, true);
       }
       __syncthreads();
       STAMP();
+      CSTAMP(0);
       mbar_wait(&sm.bbar[bsel], bsel ? parB1 : parB0);
       if (bsel) parB1 ^= 1; else parB0 ^= 1;
       mbar_wait(&sm.bar[0], parD);
       parD ^= 1;
-      gemv_pairs<HID>(bufD, n_qkv, row0_qkv, lb + BIAS_QKV, sm.xs, warp, lane,
-                      [&](int n, __half h0, __half h1) {
-                        ll_store(ws->qkv_w + (n >> 1), pack2(h0, h1), ep);
-                        if (n >= HID) {  // k / v of the current token also go to the cache for later steps
-                          const int e = (n - HID) & (HID - 1), head = e >> 6, d = e & 63;
-                          __half* c = (n < 2 * HID) ? kc : vc;
-                          *reinterpret_cast<uint32_t*>(c + ((long)head * T + pos) * HD + d) = pack2(h0, h1);
-                        }
-                      });
+      STAMP();
+      gemv_stage<HID, false>(bufD, n_qkv, lb + BIAS_QKV, sm.xs, warp, lane, sm.stage16);
+      STAMP();
       __syncthreads();
+      STAMP();
+      if (tid < (n_qkv >> 1)) {
+        const int n = row0_qkv + 2 * tid;
+        const uint32_t d = *reinterpret_cast<const uint32_t*>(sm.stage16 + 2 * tid);
+        ll_store(ws->qkv_w + (n >> 1), d, ep);
+        if (n >= HID) {  // k / v of the current token also go to the cache for later steps
+          const int e = (n - HID) & (HID - 1), head = e >> 6, dd = e & 63;
+          __half* c = (n < 2 * HID) ? kc : vc;
+          *reinterpret_cast<uint32_t*>(c + ((long)head * T + pos) * HD + dd) = d;
+        }
+      }
       if (tid == 0) {
         if (L + 1 < NL) refill(bufD, W.wqkv[L + 1], row0_qkv, n_qkv, HID, &sm.bar[0]);
         else refill(bufD, W.lm_head, row0_lm, lmD, HID, &sm.bar[0]);
       }
       STAMP();
+      CSTAMP(1);
+      // (attention-phase stamps: after the item loop, after the merge)
 
-      // ---------------- attention phase: items (chunk c, head h) = cta, cta + ncta, ...
-      for (int it = 0; item < nitems; item += ncta, it++) {
+      // ---------------- attention phase: items (chunk c, head h) = slot, slot + 2*ncta, ... of this team
+      for (int it = 0; item < nitems; item += 2 * ncta, it++) {
         const int c = item >> 4, h = item & 15;
         const int len = min(MA_ATTN_CHUNK, nkeys - c * MA_ATTN_CHUNK);
         const long base = ((long)h * T + (long)c * MA_ATTN_CHUNK) * HD;
         const int cur = pos - c * MA_ATTN_CHUNK;  // row of the current token inside this chunk (if 0 <= cur < 256)
 #pragma unroll
         for (int rho = 0; rho < 8; rho++) {
-          const int r = 32 * rho + 4 * warp + grp;
+          const int r = 32 * rho + 4 * wt + grp;
           if (r < len && it > 0 && r != cur) {  // later items were not prefetched
             kreg[rho] = ldcg16(kc + base + (long)r * HD + 8 * li);
             vreg[rho] = ldcg16(vc + base + (long)r * HD + 8 * li);
@@ -379,17 +504,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         // q of this head and, for the chunk that holds it, k / v of the current token: flagged words
         float qf[8];
         {
-          const uint2 d0 = ll_wait2(ws->qkv_w + (h * HD + 8 * li) / 2, ep, err);
-          const uint2 d1 = ll_wait2(ws->qkv_w + (h * HD + 8 * li) / 2 + 2, ep, err);
-          unpack8(make_uint4(d0.x, d0.y, d1.x, d1.y), qf);
+          uint2 d[2];
+          ll_wait_units<2>(ws->qkv_w + (h * HD + 8 * li) / 2, 1, ep, d, err);
+          unpack8(make_uint4(d[0].x, d[0].y, d[1].x, d[1].y), qf);
         }
         if (cur >= 0 && cur < MA_ATTN_CHUNK) {
           const int rho_c = cur >> 5, gl_c = cur & 31;
-          if (4 * warp + grp == gl_c) {
-            const uint2 k0 = ll_wait2(ws->qkv_w + (HID + h * HD + 8 * li) / 2, ep, err);
-            const uint2 k1 = ll_wait2(ws->qkv_w + (HID + h * HD + 8 * li) / 2 + 2, ep, err);
-            const uint2 v0 = ll_wait2(ws->qkv_w + (2 * HID + h * HD + 8 * li) / 2, ep, err);
-            const uint2 v1 = ll_wait2(ws->qkv_w + (2 * HID + h * HD + 8 * li) / 2 + 2, ep, err);
+          if (4 * wt + grp == gl_c) {
+            uint2 kk[2], vv[2];
+            ll_wait_units<2>(ws->qkv_w + (HID + h * HD + 8 * li) / 2, 1, ep, kk, err);
+            ll_wait_units<2>(ws->qkv_w + (2 * HID + h * HD + 8 * li) / 2, 1, ep, vv, err);
+            const uint2 k0 = kk[0], k1 = kk[1], v0 = vv[0], v1 = vv[1];
 #pragma unroll
             for (int rho = 0; rho < 8; rho++)
               if (rho == rho_c) {
@@ -402,7 +527,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         float lmax = -INFINITY;
 #pragma unroll
         for (int rho = 0; rho < 8; rho++) {
-          const int r = 32 * rho + 4 * warp + grp;
+          const int r = 32 * rho + 4 * wt + grp;
           float kf[8];
           unpack8(kreg[rho], kf);
           float p = 0.0f;
@@ -415,18 +540,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
           if (r < len) lmax = fmaxf(lmax, sreg[rho]);
         }
         lmax = warp_max(lmax);
-        __syncthreads();  // previous users of wmax / ared are done
-        if (lane == 0) sm.wmax[warp] = lmax;
-        __syncthreads();
-        float cmax = sm.wmax[0];
+        team_sync(team);  // previous users of wmax / ared of this team are done
+        if (lane == 0) sm.wmax[team][wt] = lmax;
+        team_sync(team);
+        float cmax = sm.wmax[team][0];
 #pragma unroll
-        for (int w2 = 1; w2 < 8; w2++) cmax = fmaxf(cmax, sm.wmax[w2]);
+        for (int w2 = 1; w2 < 8; w2++) cmax = fmaxf(cmax, sm.wmax[team][w2]);
         float l = 0.0f, o[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) o[j] = 0.0f;
 #pragma unroll
         for (int rho = 0; rho < 8; rho++) {
-          const int r = 32 * rho + 4 * warp + grp;
+          const int r = 32 * rho + 4 * wt + grp;
           if (r < len) {
             const float e = ma_exp(fsub(sreg[rho], cmax));
             l = fadd(l, e);
@@ -446,37 +571,38 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         }
         if (grp == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) sm.ared[warp][8 * li + j] = o[j];
-          if (li == 0) sm.ared[warp][64] = l;
+          for (int j = 0; j < 8; j++) sm.ared[team][wt][8 * li + j] = o[j];
+          if (li == 0) sm.ared[team][wt][64] = l;
         }
-        __syncthreads();
-        if (tid < 65) {
+        team_sync(team);
+        if (tl < 65) {
           float x[8];
 #pragma unroll
-          for (int w2 = 0; w2 < 8; w2++) x[w2] = sm.ared[w2][tid];
+          for (int w2 = 0; w2 < 8; w2++) x[w2] = sm.ared[team][w2][tl];
           const float rsum = fadd(fadd(fadd(x[0], x[1]), fadd(x[2], x[3])), fadd(fadd(x[4], x[5]), fadd(x[6], x[7])));
           uint2* part = ws->part_w + ((long)h * MAX_CHUNKS + c) * PARTF;
-          ll_store(part + (tid < 64 ? tid : 65), __float_as_uint(rsum), ep);
-          if (tid == 64) ll_store(part + 64, __float_as_uint(cmax), ep);
+          ll_store(part + (tl < 64 ? tl : 65), __float_as_uint(rsum), ep);
+          if (tl == 64) ll_store(part + 64, __float_as_uint(cmax), ep);
         }
       }
-      // merge of the chunks of head h by the CTA that owns item (chunk 0, head h): ascending order
-      if (cta < NHEAD) {
-        const int h = cta;
+      STAMP();
+      CSTAMP(2);
+      // merge of the chunks of head h by team 0 of the CTA that owns item (chunk 0, head h): ascending order
+      if (team == 0 && ncta - 1 - cta < NHEAD) {   // the team that owns item (chunk 0, head h)
+        const int h = ncta - 1 - cta;
         const uint2* part = ws->part_w + (long)h * MAX_CHUNKS * PARTF;
-        __syncthreads();
-        // stage {max, sum} of every chunk in shared memory (parallel polls), then each of 64 threads walks its dim
-        float* stage = reinterpret_cast<float*>(sm.xs);  // 2 * nch floats
-        for (int i = tid; i < 2 * nch; i += MG_THREADS)
+        float* stage = sm.cstage + team * 2 * MAX_CHUNKS;  // {max, sum} of every chunk: 2*nch floats per team
+        team_sync(team);
+        for (int i = tl; i < 2 * nch; i += TEAM)
           stage[i] = __uint_as_float(ll_wait1(part + (i >> 1) * PARTF + 64 + (i & 1), ep, err));
-        __syncthreads();
-        if (tid < 64) {
+        team_sync(team);
+        if (tl < 64) {
           float M = -INFINITY;
           for (int cc = 0; cc < nch; cc++) M = fmaxf(M, stage[2 * cc]);
           float Lsum = 0.0f, O = 0.0f;
-          float oc = __uint_as_float(ll_wait1(part + tid, ep, err));
+          float oc = __uint_as_float(ll_wait1(part + tl, ep, err));
           for (int cc = 0; cc < nch; cc++) {
-            const float onext = (cc + 1 < nch) ? __uint_as_float(ll_wait1(part + (cc + 1) * PARTF + tid, ep, err)) : 0.0f;
+            const float onext = (cc + 1 < nch) ? __uint_as_float(ll_wait1(part + (cc + 1) * PARTF + tl, ep, err)) : 0.0f;
             const float wgt = ma_exp(fsub(stage[2 * cc], M));
             Lsum = ffma(stage[2 * cc + 1], wgt, Lsum);
             O = ffma(oc, wgt, O);
@@ -484,21 +610,23 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
           }
           const __half r = __float2half_rn(__fdiv_rn(O, Lsum));
           const __half r2 = __shfl_down_sync(0xffffffffu, r, 1);
-          if ((tid & 1) == 0) ll_store(ws->attn_w + (h * HD + tid) / 2, pack2(r, r2), ep);
+          if ((tl & 1) == 0) ll_store(ws->attn_w + (h * HD + tl) / 2, pack2(r, r2), ep);
         }
-        __syncthreads();
       }
       STAMP();
+      CSTAMP(3);
 
       // ---------------- out_proj phase
       if (n_out > 0) {
         ll_gather(ws->attn_w, HID, ep, sm.xs, err);
         __syncthreads();
         mbar_wait(&sm.bar[1], parC);
-        gemv_pairs<HID>(bufC, n_out, row0_out, lb + BIAS_OUT, sm.xs, warp, lane,
-                        [&](int n, __half h0, __half h1) { ll_store(ws->ya_w + (n >> 1), pack2(h0, h1), ep); });
+        gemv_stage<HID, false>(bufC, n_out, lb + BIAS_OUT, sm.xs, warp, lane, sm.stage16);
         __syncthreads();
+        if (tid < (n_out >> 1))
+          ll_store(ws->ya_w + ((row0_out + 2 * tid) >> 1), *reinterpret_cast<const uint32_t*>(sm.stage16 + 2 * tid), ep);
       } else {
+        __syncthreads();
         mbar_wait(&sm.bar[1], parC);
       }
       parC ^= 1;
@@ -507,121 +635,98 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         else refill(bufC, W.lm_head, row0_lm + a.rows_qkv, lmC, HID, &sm.bar[1]);
       }
       STAMP();
+      CSTAMP(4);
 
       // ---------------- fc1 phase: input = LN1(hres + out_proj)
       {
-        const float4 hv = *reinterpret_cast<const float4*>(sm.hres + 4 * tid);
-        const uint2 d = ll_wait2(ws->ya_w + 2 * tid, ep, err);
-        const __half2* hh = reinterpret_cast<const __half2*>(&d);
-        const float2 p0 = __half22float2(hh[0]), p1 = __half22float2(hh[1]);
-        float v[4] = {fadd(hv.x, p0.x), fadd(hv.y, p0.y), fadd(hv.z, p1.x), fadd(hv.w, p1.y)};
+        float v[4];
+        residual_in(ws->ya_w, ep, v);
         mbar_wait(&sm.lnbar[0], parL1);
         parL1 ^= 1;
-        layernorm4(v, sm.ln1, sm.ln1 + HID, MA_LN_EPS, HID, sm.red);
+        layernorm_1024(v, sm.ln1, sm.ln1 + HID, sm.red, tid);
         __syncthreads();
         if (tid == 0) fill_ln(sm.ln1, W.ln1g[(L + 1) % NL], W.ln1b[(L + 1) % NL], &sm.lnbar[0]);
-        *reinterpret_cast<float4*>(sm.hres + 4 * tid) = make_float4(v[0], v[1], v[2], v[3]);
-        __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-        uint2 uo;
-        uo.x = *reinterpret_cast<uint32_t*>(&h0);
-        uo.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(sm.xs + 4 * tid) = uo;
+        publish_x(v, true);
       }
       __syncthreads();
       mbar_wait(&sm.bar[2], parA);
       parA ^= 1;
-      gemv_pairs<HID>(bufA, n_fc1, row0_fc1, lb + BIAS_FC1, sm.xs, warp, lane,
-                      [&](int n, __half h0, __half h1) {
-                        if (__half2float(h0) < 0.0f) h0 = __float2half_rn(0.0f);
-                        if (__half2float(h1) < 0.0f) h1 = __float2half_rn(0.0f);
-                        ll_store(ws->f_w + (n >> 1), pack2(h0, h1), ep);
-                      });
+      gemv_stage<HID, true>(bufA, n_fc1, lb + BIAS_FC1, sm.xs, warp, lane, sm.stage16);
       __syncthreads();
+      if (tid < (n_fc1 >> 1))
+        ll_store(ws->f_w + ((row0_fc1 + 2 * tid) >> 1), *reinterpret_cast<const uint32_t*>(sm.stage16 + 2 * tid), ep);
       if (tid == 0) {
         if (L + 1 < NL) refill(bufA, W.w1[L + 1], row0_fc1, n_fc1, HID, &sm.bar[2]);
         else refill(bufA, W.lm_head, row0_lm + a.rows_qkv + a.rows_out, lmA, HID, &sm.bar[2]);
       }
       STAMP();
+      CSTAMP(5);
 
       // ---------------- fc2 phase
       if (n_fc2 > 0) {
         ll_gather(ws->f_w, FFN, ep, sm.xs, err);
         __syncthreads();
         mbar_wait(&sm.bar[3], parB);
-        gemv_pairs<FFN>(bufB, n_fc2, row0_fc2, lb + BIAS_FC2, sm.xs, warp, lane,
-                        [&](int n, __half h0, __half h1) { ll_store(ws->yb_w + (n >> 1), pack2(h0, h1), ep); });
+        gemv_stage<FFN, false>(bufB, n_fc2, lb + BIAS_FC2, sm.xs, warp, lane, sm.stage16);
         __syncthreads();
+        if (tid < (n_fc2 >> 1))
+          ll_store(ws->yb_w + ((row0_fc2 + 2 * tid) >> 1), *reinterpret_cast<const uint32_t*>(sm.stage16 + 2 * tid), ep);
       } else {
+        __syncthreads();
         mbar_wait(&sm.bar[3], parB);
       }
       parB ^= 1;
       if (tid == 0) {
         refill(bufB, W.w2[(L + 1 < NL) ? L + 1 : 0], row0_fc2, n_fc2, FFN, &sm.bar[3]);
-        // the bias buffer of this layer is free (every warp passed the __syncthreads above or has no fc2 rows):
-        // refill it with the biases of the layer that uses it next (L + 2, wrapping into the next token)
+        // the bias buffer of this layer is free: refill it for the layer instance that uses it next (L + 2)
+        fill_bias(sm.bias[bsel], ws->bias_cta + ((size_t)((L + 2) % NL) * 160 + cta) * 128, &sm.bbar[bsel]);
       }
-      __syncthreads();
-      if (tid == 0) fill_bias(sm.bias[bsel], ws->bias_cta + ((size_t)((L + 2) % NL) * 160 + cta) * 128, &sm.bbar[bsel]);
       lc++;
       STAMP();
+      CSTAMP(6);
     }
 
     // ---------------- lm_head on LN2 of the last layer + greedy pick
     const uint32_t epc = (uint32_t)(a.step_base + step) + 1u;
     {
-      const float4 hv = *reinterpret_cast<const float4*>(sm.hres + 4 * tid);
-      const uint2 d = ll_wait2(ws->yb_w + 2 * tid, ep0 + (uint32_t)NL - 1u, err);
-      const __half2* hh = reinterpret_cast<const __half2*>(&d);
-      const float2 p0 = __half22float2(hh[0]), p1 = __half22float2(hh[1]);
-      float v[4] = {fadd(hv.x, p0.x), fadd(hv.y, p0.y), fadd(hv.z, p1.x), fadd(hv.w, p1.y)};
+      float v[4];
+      residual_in(ws->yb_w, ep0 + (uint32_t)NL - 1u, v);
       mbar_wait(&sm.lnbar[1], parL2);
       parL2 ^= 1;
-      layernorm4(v, sm.ln2, sm.ln2 + HID, MA_LN_EPS, HID, sm.red);
+      layernorm_1024(v, sm.ln2, sm.ln2 + HID, sm.red, tid);
       __syncthreads();
       if (tid == 0) fill_ln(sm.ln2, W.ln2g[0], W.ln2b[0], &sm.lnbar[1]);
-      __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-      uint2 uo;
-      uo.x = *reinterpret_cast<uint32_t*>(&h0);
-      uo.y = *reinterpret_cast<uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(sm.xs + 4 * tid) = uo;
+      publish_x(v, false);
     }
     __syncthreads();
     mbar_wait(&sm.bar[0], parD);
     mbar_wait(&sm.bar[1], parC);
     mbar_wait(&sm.bar[2], parA);
     parD ^= 1; parC ^= 1; parA ^= 1;
+    gemv_stage<HID, false>(bufD, n_lm, nullptr, sm.xs, warp, lane, sm.stage16);
+    __syncthreads();
     float bestv = -INFINITY;
     int besti = 0x7fffffff;
-    {
-      // n_lm may be odd (vocab 8195): the last pair's second row then reads stale shared memory and is ignored
-      const int n_even = (n_lm + 1) & ~1;
-      // up to 56 rows = 28 pairs: gemv_pairs covers 4 pairs per warp (32), enough for rows_lm <= 64
-      gemv_pairs<HID>(bufD, n_even, row0_lm, nullptr, sm.xs, warp, lane, [&](int n, __half h0, __half h1) {
-        const bool two = (n + 1 < row0_lm + n_lm);
-        if (a.logits_out) {
-          a.logits_out[(long)gen * W.vocab + n] = h0;
-          if (two) a.logits_out[(long)gen * W.vocab + n + 1] = h1;
-        }
-        const float v0 = __half2float(h0);
-        if (v0 > bestv || (v0 == bestv && n < besti)) { bestv = v0; besti = n; }
-        if (two) {
-          const float v1 = __half2float(h1);
-          if (v1 > bestv || (v1 == bestv && n + 1 < besti)) { bestv = v1; besti = n + 1; }
-        }
-      });
+    if (tid < n_lm) {
+      const __half hv = sm.stage16[tid];
+      if (a.logits_out) a.logits_out[(long)gen * W.vocab + row0_lm + tid] = hv;
+      bestv = __half2float(hv);
+      besti = row0_lm + tid;
     }
-    {  // lanes 0 and 16 each tracked the rows they emitted
-      const float ov = __shfl_xor_sync(0xffffffffu, bestv, 16);
-      const int oi = __shfl_xor_sync(0xffffffffu, besti, 16);
-      if (ov > bestv || (ov == bestv && oi < besti)) { bestv = ov; besti = oi; }
+    if (warp < 2) {  // rows_lm <= 64: the candidates live in the first two warps
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ov > bestv || (ov == bestv && oi < besti)) { bestv = ov; besti = oi; }
+      }
+      if (lane == 0) { sm.bval[warp] = bestv; sm.bidx[warp] = besti; }
     }
-    if (lane == 0) { sm.bval[warp] = bestv; sm.bidx[warp] = besti; }
     __syncthreads();
     if (tid == 0) {
       float bv = sm.bval[0];
       int bi = sm.bidx[0];
-      for (int w2 = 1; w2 < MG_WARPS; w2++)
-        if (sm.bval[w2] > bv || (sm.bval[w2] == bv && sm.bidx[w2] < bi)) { bv = sm.bval[w2]; bi = sm.bidx[w2]; }
+      if (sm.bval[1] > bv || (sm.bval[1] == bv && sm.bidx[1] < bi)) { bv = sm.bval[1]; bi = sm.bidx[1]; }
       __threadfence();  // publish this step's KV-cache rows before the step's final hand-off
       ll_store(ws->cand_w + 2 * cta, __float_as_uint(bv), epc);
       ll_store(ws->cand_w + 2 * cta + 1, (uint32_t)bi, epc);
@@ -633,11 +738,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     {
       float bv = -INFINITY;
       int bi = 0x7fffffff;
-      for (int i = tid; i < ncta; i += MG_THREADS) {
-        const uint2 d = ll_wait2(ws->cand_w + 2 * i, epc, err);
-        const float v = __uint_as_float(d.x);
-        const int ix = (int)d.y;
-        if (v > bv || (v == bv && ix < bi)) { bv = v; bi = ix; }
+      if (tid < ncta) {
+        const uint2 d = ll_wait2(ws->cand_w + 2 * tid, epc, err);
+        bv = __uint_as_float(d.x);
+        bi = (int)d.y;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -736,6 +840,7 @@ int mega_prepare(const ma_decoder_weights* w, void* mega_ws, cudaStream_t st) {
 
 int mega_error_flag_offset() { return (int)offsetof(MegaWs, error); }
 int mega_trace_offset() { return (int)offsetof(MegaWs, trace); }
+int mega_trace_cta_offset() { return (int)offsetof(MegaWs, trace_cta); }
 
 int mega_enqueue(const ma_decoder_weights* w, SeqState s, int tmax, __half* kv, void* mega_ws, const SampleArgs& sa,
                  int n_steps, int step_base, int trace, cudaStream_t st) {

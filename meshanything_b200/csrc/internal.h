@@ -79,5 +79,6 @@ int mega_enqueue(const ma_decoder_weights* w, SeqState s, int tmax, __half* kv, 
                  int n_steps, int step_base, int trace, cudaStream_t st);
 int mega_error_flag_offset();
 int mega_trace_offset();
+int mega_trace_cta_offset();
 
 }  // namespace ma

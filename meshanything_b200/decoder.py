@@ -135,3 +135,9 @@ class Generator:
         capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 1, buf, 8 * n),
                    "ma_decoder_debug")
         return list(buf)
+
+    def mega_trace_cta(self, n_cta: int = 147):
+        buf = (C.c_uint64 * (160 * 8))()
+        capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 2, buf, 8 * 160 * 8),
+                   "ma_decoder_debug")
+        return [[buf[c * 8 + k] for k in range(8)] for c in range(n_cta)]

@@ -18,8 +18,8 @@ torch.cuda.synchronize()
 print('error flag', gen.mega_error())
 tr = gen.mega_trace(1280)
 # per layer stamps: [qkv: prologue_done, weights_ready, compute+refill done, barrier done], attn, out, fc1, fc2 (1 each)
-per_layer = 6
-names = ['qkv.prologue', 'qkv.compute', 'attn', 'out', 'fc1', 'fc2']
+per_layer = 10
+names = ['qkv.prologue', 'qkv.wait', 'qkv.gemv', 'qkv.sync', 'qkv.emit+refill', 'attn.items', 'attn.merge', 'out', 'fc1', 'fc2']
 agg = collections.defaultdict(list)
 i = 1
 for L in range(NL):
@@ -30,3 +30,13 @@ for k in names:
     v = agg[k]
     print(f'{k:14s} avg {sum(v)/len(v):6.2f} us  min {min(v):6.2f} max {max(v):6.2f}')
 print('lm+pick', (tr[i] - tr[i - 1]) / 1000.0, 'us; step total', (tr[i] - tr[0]) / 1000.0, 'us')
+
+# per-CTA skew at (step 1, layer 12): time each CTA reaches the end of each phase, relative to the earliest CTA
+tc = gen.mega_trace_cta(147)
+import statistics
+labels = ['x ready(qkv in)', 'qkv done', 'attn items done', 'attn merge done', 'out done', 'fc1 done', 'fc2 done']
+base = min(r[0] for r in tc if r[0])
+for k, lab in enumerate(labels):
+    col = [(r[k] - base) / 1000.0 for r in tc if r[k]]
+    srt = sorted(range(len(col)), key=lambda i: col[i])
+    print(f'{lab:18s} min {min(col):6.2f} med {statistics.median(col):6.2f} max {max(col):6.2f} us   slowest CTAs {srt[-3:]} fastest {srt[:3]}')
