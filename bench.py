@@ -161,6 +161,10 @@ def main():
     # ------------------------------------------------------------------ our arm
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    # stdout must carry exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = parallel.init_from_env()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -298,7 +302,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "check": {"first_ids": ids[0, :8].cpu().tolist()},
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         torch.distributed.destroy_process_group()
 

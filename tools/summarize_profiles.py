@@ -1,0 +1,52 @@
+"""Turns the raw ncu outputs in gpurun_out/ into the committed summaries under profiles/ (run in the dev container).
+usage: python tools/summarize_profiles.py <round tag, e.g. r01>"""
+import collections, csv, json, os, re, subprocess, sys
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out = []
+
+def launches(path):
+    if not os.path.exists(path):
+        return
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.defaultdict(list)
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", ""))
+        u = row["Metric Unit"]
+        v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v * 1e6 if u == "s" else v
+        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
+        agg[name + " grid=" + row["Grid Size"]].append(v)
+    tot = sum(sum(v) for v in agg.values())
+    out.append(f"## Launch list ({os.path.basename(path)}; `ncu --metrics gpu__time_duration.sum --clock-control none`, cold cache, serialised)\n")
+    out.append("| kernel | launches | avg us | share |\n|---|---:|---:|---:|")
+    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        out.append(f"| `{k}` | {len(v)} | {sum(v)/len(v):.2f} | {100*sum(v)/tot:.1f} % |")
+    out.append(f"\ntotal {tot/1000:.2f} ms over {sum(len(v) for v in agg.values())} launches\n")
+
+def full(path, title):
+    if not os.path.exists(path):
+        return
+    r = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
+    rows = list(csv.reader(r.stdout.splitlines()))
+    hdr, units = rows[0], rows[1]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+            "dram__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__grid_size",
+            "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+            "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+    out.append(f"## {title} (`{os.path.basename(path)}`, `ncu --set full --clock-control none --import-source on`)\n")
+    for line in rows[2:]:
+        name = line[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        out.append(f"kernel `{name[:80]}`\n\n| metric | value |\n|---|---|")
+        for w in want:
+            if w in hdr:
+                i = hdr.index(w)
+                out.append(f"| {w} | {line[i]} {units[i]} |")
+        out.append("")
+
+launches(f"gpurun_out/launches_{tag}.csv")
+full(f"gpurun_out/prof_mega_{tag}.ncu-rep", "Persistent decode kernel")
+os.makedirs("profiles", exist_ok=True)
+open(f"profiles/ncu_summary_{tag}.md", "w").write("\n".join(out) + "\n")
+print("\n".join(out)[:3000])
