@@ -591,23 +591,68 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
       if (team == 0 && ncta - 1 - cta < NHEAD) {   // the team that owns item (chunk 0, head h)
         const int h = ncta - 1 - cta;
         const uint2* part = ws->part_w + (long)h * MAX_CHUNKS * PARTF;
-        float* stage = sm.cstage + team * 2 * MAX_CHUNKS;  // {max, sum} of every chunk: 2*nch floats per team
+        // All 66 words of every chunk are staged in shared memory by the 256 threads of the team with their polls in
+        // flight together (blocks of up to 31 chunks = the 8 KB of xs, idle during attention).  The chunk weights
+        // exp(m_c - M) are computed once per chunk; then 64 threads run the ascending fma chain of the canonical merge.
+        float* ost = reinterpret_cast<float*>(sm.xs);          // [chunk][66]
+        float* wgt = sm.cstage + team * 2 * MAX_CHUNKS;         // [chunk]
+        float* mst = wgt + MAX_CHUNKS;                          // [chunk] maxima (needed before any weight)
+        const bool single = nch <= 31;   // one staging round also brings the maxima: no separate round for them
         team_sync(team);
-        for (int i = tl; i < 2 * nch; i += TEAM)
-          stage[i] = __uint_as_float(ll_wait1(part + (i >> 1) * PARTF + 64 + (i & 1), ep, err));
-        team_sync(team);
-        if (tl < 64) {
+        if (!single) {
+          for (int i = tl; i < nch; i += TEAM) mst[i] = __uint_as_float(ll_wait1(part + (long)i * PARTF + 64, ep, err));
+          team_sync(team);
           float M = -INFINITY;
-          for (int cc = 0; cc < nch; cc++) M = fmaxf(M, stage[2 * cc]);
-          float Lsum = 0.0f, O = 0.0f;
-          float oc = __uint_as_float(ll_wait1(part + tl, ep, err));
-          for (int cc = 0; cc < nch; cc++) {
-            const float onext = (cc + 1 < nch) ? __uint_as_float(ll_wait1(part + (cc + 1) * PARTF + tl, ep, err)) : 0.0f;
-            const float wgt = ma_exp(fsub(stage[2 * cc], M));
-            Lsum = ffma(stage[2 * cc + 1], wgt, Lsum);
-            O = ffma(oc, wgt, O);
-            oc = onext;
+          for (int cc = 0; cc < nch; cc++) M = fmaxf(M, mst[cc]);
+          for (int i = tl; i < nch; i += TEAM) wgt[i] = ma_exp(fsub(mst[i], M));
+        }
+        float Lsum = 0.0f, O = 0.0f;
+        for (int c0 = 0; c0 < nch; c0 += 31) {
+          const int nb = min(31, nch - c0), nw = nb * PARTF;
+          {
+            uint2 w[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int i = tl + TEAM * k;
+              if (i < nw) w[k] = ll_load1(part + (long)c0 * PARTF + i);
+            }
+            unsigned spins = 0;
+            for (;;) {
+              bool ok = true;
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                const int i = tl + TEAM * k;
+                if (i < nw && w[k].y != ep) {
+                  ok = false;
+                  w[k] = ll_load1(part + (long)c0 * PARTF + i);
+                }
+              }
+              if (ok) break;
+              if (++spins > SPIN_LIMIT) { *err = 1; break; }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int i = tl + TEAM * k;
+              if (i < nw) ost[i] = __uint_as_float(w[k].x);
+            }
           }
+          team_sync(team);
+          if (single) {
+            float M = -INFINITY;
+            for (int cc = 0; cc < nch; cc++) M = fmaxf(M, ost[cc * PARTF + 64]);
+            for (int i = tl; i < nch; i += TEAM) wgt[i] = ma_exp(fsub(ost[i * PARTF + 64], M));
+            team_sync(team);
+          }
+          if (tl < 64) {
+            for (int cc = 0; cc < nb; cc++) {
+              const float wc = wgt[c0 + cc];
+              Lsum = ffma(ost[cc * PARTF + 65], wc, Lsum);
+              O = ffma(ost[cc * PARTF + tl], wc, O);
+            }
+          }
+          team_sync(team);
+        }
+        if (tl < 64) {
           const __half r = __float2half_rn(__fdiv_rn(O, Lsum));
           const __half r2 = __shfl_down_sync(0xffffffffu, r, 1);
           if ((tl & 1) == 0) ll_store(ws->attn_w + (h * HD + tl) / 2, pack2(r, r2), ep);
@@ -872,6 +917,12 @@ int mega_enqueue(const ma_decoder_weights* w, SeqState s, int tmax, __half* kv, 
   const int grid = (FFN + a.rows_fc1 - 1) / a.rows_fc1;
   if (grid > sms || (w->vocab + a.rows_lm - 1) / a.rows_lm != grid || grid < NHEAD) {
     set_error("mega: unsupported SM count %d (grid %d)", sms, grid);
+    return 1;
+  }
+  // the merging teams (last 16 CTAs) stage partials in xs while the other team may run ahead: those CTAs must not
+  // own out_proj / fc2 rows (whose phases write xs from all threads)
+  if (grid - NHEAD < (HID + a.rows_out - 1) / a.rows_out) {
+    set_error("mega: the last %d CTAs must not own out_proj rows (grid %d)", NHEAD, grid);
     return 1;
   }
   const size_t smem = sizeof(MegaSmem) + ((size_t)(a.rows_qkv + a.rows_out + a.rows_fc1) * HID + (size_t)a.rows_fc2 * FFN) * 2;
