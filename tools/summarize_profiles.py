@@ -50,3 +50,34 @@ full(f"gpurun_out/prof_mega_{tag}.ncu-rep", "Persistent decode kernel")
 os.makedirs("profiles", exist_ok=True)
 open(f"profiles/ncu_summary_{tag}.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:3000])
+
+# ---- profiles/README.md from the bench line
+bj = f"gpurun_out/bench_{tag}.json"
+if os.path.exists(bj) and os.path.getsize(bj) > 0:
+    d = json.load(open(bj))
+    import shutil
+    shutil.copy(bj, f"profiles/bench_{tag}.json")
+    r = d["roofline"]
+    md = [f"# profiles — round {tag}\n",
+          "All numbers from `gpurun` on one B200 of the pool (SM clock %s MHz during the timed region, reasons %s).\n" % (
+              d["clocks"]["sm_mhz"], d["clocks"]["reasons"]),
+          "## bench.py (default: batch 1, 800 faces, greedy; `bench_%s.json`)\n" % tag,
+          "| quantity | value |\n|---|---|",
+          f"| face-tokens/s, inputs resident (`value`) | {d['value']:.1f} |",
+          f"| face-tokens/s, host in / host out (`e2e`) | {d['e2e']['value']:.1f} |",
+          f"| ms per step (one 800-face mesh) | {d['ms_per_step']:.1f} |",
+          f"| stage split (ms) | encoder {d['config']['stage_ms']['encoder']:.2f}, generate {d['config']['stage_ms']['generate']:.1f}, detokenize+rest {d['config']['stage_ms']['detokenize_and_rest']:.2f} |",
+          f"| decode loop: us per token (average over contexts 258..7458) | {r['us_per_step_avg']:.1f} |",
+          f"| decode loop: achieved HBM GB/s (algorithmic bytes) / measured peak | {r['achieved']:.0f} / {r['peak']:.1f} = **{r['frac']:.3f}** |",
+          f"| short context (~357..557): us per token, fraction of peak | {r['short_context']['us_per_step']:.1f}, {r['short_context']['frac']:.3f} |",
+          f"| prefill (257 prefix tokens) | {r['prefill_ms']:.2f} ms |",
+          f"| CPU baseline (oracle, {d['cpu_baseline']['cores'] if d.get('cpu_baseline') else '?'} cores) | {d['cpu_baseline']['value'] if d.get('cpu_baseline') else float('nan'):.1f} tokens/s |",
+          f"| kernels launched in the timed region | {d['gpu_launches']} |",
+          "",
+          "Files: `ncu_summary_%s.md` (launch list + full-capture metrics), `microbench_%s.txt` (hand-off / GEMV micro-benchmarks), "
+          "`mega_trace_%s.txt` (phase timeline of the persistent kernel from its own globaltimer stamps: short and long context).\n" % (tag, tag, tag)]
+    open("profiles/README.md", "w").write("\n".join(md))
+    print("\n".join(md))
+if os.path.exists(f"gpurun_out/mega_trace_{tag}.txt"):
+    import shutil
+    shutil.copy(f"gpurun_out/mega_trace_{tag}.txt", f"profiles/mega_trace_{tag}.txt")
