@@ -119,6 +119,15 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
 int ma_decoder_debug(void* ws, int B, int tmax, int what, void* host_out, int nbytes);
 
 
+/* Same contract as ma_linear_f16 on the tcgen05 tensor cores (TMA-fed, accumulator in TMEM): fp16 in, fp32
+ * accumulate in the hardware's order (NOT the canonical order: results agree with ma_linear_f16 to fp32 rounding,
+ * not bit for bit).  M >= 64, N % 128 == 0, K % 64 == 0.  Used by ma_encoder_forward / ma_detokenize. */
+int ma_linear_tc_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
+                     int epilogue, void* stream);
+/* 1 (default): encoder / detokenizer GEMMs run on the tensor cores; 0: canonical CUDA-core kernel.  Returns the
+ * previous setting. */
+int ma_set_tensor_cores(int enable);
+
 /* ---- Michelangelo point-cloud encoder (a1-a8) ----------------------------------------------- */
 
 typedef struct { /* ResidualAttentionBlock, transformer_blocks.py:77-115 (qkv_bias: false) */

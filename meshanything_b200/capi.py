@@ -39,7 +39,7 @@ EXPORTS = [
     "ma_abi_version", "ma_last_error", "ma_launch_count", "ma_linear_f16", "ma_layernorm",
     "ma_attention_scratch_bytes", "ma_attention_f16", "ma_kv_cache_bytes", "ma_decoder_workspace_bytes",
     "ma_decode_generate", "ma_decoder_debug", "ma_encoder_workspace_bytes", "ma_encoder_forward",
-    "ma_detokenize_workspace_bytes", "ma_detokenize",
+    "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores",
 ]
 
 
@@ -78,6 +78,8 @@ def lib():
     L.ma_detokenize_workspace_bytes.argtypes = [C.c_int, C.c_int]
     L.ma_detokenize_workspace_bytes.restype = C.c_size_t
     L.ma_detokenize.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]
+    L.ma_linear_tc_f16.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
+    L.ma_set_tensor_cores.argtypes = [C.c_int]
     if L.ma_abi_version() != 1:
         raise RuntimeError("libmeshanything_b200.so: ABI version mismatch")
     _lib = L
@@ -117,6 +119,17 @@ def linear_f16(w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor, e
         out = torch.empty((M, N), dtype=torch.float16, device=x.device)
     check(lib().ma_linear_f16(ptr(w), ptr(bias), ptr(x), x.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
                               stream_ptr()), "ma_linear_f16")
+    return out
+
+
+def linear_tc_f16(w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor, epilogue: int = EPI_NONE) -> torch.Tensor:
+    """fp16(x @ w.T + bias) on the tcgen05 tensor cores (hardware accumulation order)."""
+    _need_cuda(w, bias, x)
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    check(lib().ma_linear_tc_f16(ptr(w), ptr(bias), ptr(x), x.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
+                                 stream_ptr()), "ma_linear_tc_f16")
     return out
 
 

@@ -69,27 +69,36 @@ static EncWs carve_enc(void* base, int Bc) {
 
 #define TRY(x) do { if (x) return 1; } while (0)
 
+static int g_use_tc = 1;  // dense contractions of the encoder / detokenizer on tcgen05 (ma_set_tensor_cores)
+
+// nn.Linear of the tolerance-checked stages: tensor cores when the shape allows, canonical CUDA-core kernel otherwise
+static int enc_linear(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
+                      int K, int epi, cudaStream_t st) {
+  if (g_use_tc && linear_tc_supported(M, N, K, ldx, ldy, x, W, y)) return launch_linear_tc(W, bias, x, ldx, y, ldy, M, N, K, epi, st);
+  return launch_linear(W, bias, x, ldx, y, ldy, M, N, K, epi, st);
+}
+
 // x += c_proj(attn(c_qkv(ln_1 x))) ; x += c_proj(gelu(c_fc(ln_2 x)))   (transformer_blocks.py:109-112)
 // n tokens per shape; residual stream fp32 (x32) or fp16 (x16r).
 static int miche_block(const ma_miche_block& b, const EncWs& w, int Bc, int n, bool fp16_stream, cudaStream_t st) {
   const int M = Bc * n;
   if (fp16_stream) TRY(launch_layernorm(nullptr, w.x16r, b.ln1_g, b.ln1_b, MA_LN_EPS, M, EW, nullptr, w.ln16, st));
   else TRY(launch_layernorm(w.x32, nullptr, b.ln1_g, b.ln1_b, MA_LN_EPS, M, EW, nullptr, w.ln16, st));
-  TRY(launch_linear((const __half*)b.c_qkv_w, nullptr, w.ln16, EW, w.qkv16, 3 * EW, M, 3 * EW, EW, MA_EPI_NONE, st));
+  TRY(enc_linear((const __half*)b.c_qkv_w, nullptr, w.ln16, EW, w.qkv16, 3 * EW, M, 3 * EW, EW, MA_EPI_NONE, st));
   // qkv viewed [B,n,12,192]: head h = columns 192h .. 192h+191 = q | k | v  (transformer_blocks.py:60-62)
   TRY(launch_scatter_heads(w.qkv16, 3 * EW, 0, 192, EH, 1, 1, w.qh, M, st));
   TRY(launch_scatter_heads(w.qkv16, 3 * EW, 64, 192, EH, n, n, w.kh, M, st));
   TRY(launch_scatter_heads(w.qkv16, 3 * EW, 128, 192, EH, n, n, w.vh, M, st));
   TRY(launch_fill_i32(w.nkeys, n, M, st));
   TRY(launch_attention(w.qh, EW, w.kh, w.vh, n, EH, n, nullptr, w.nkeys, n, M, 0.125f, w.attn16, EW, w.attn_scratch, st));
-  TRY(launch_linear((const __half*)b.c_proj_w, (const __half*)b.c_proj_b, w.attn16, EW, w.y16, EW, M, EW, EW,
+  TRY(enc_linear((const __half*)b.c_proj_w, (const __half*)b.c_proj_b, w.attn16, EW, w.y16, EW, M, EW, EW,
                     MA_EPI_NONE, st));
   TRY(launch_residual_add(fp16_stream ? nullptr : w.x32, w.x16r, w.y16, (long)M * EW, st));
   if (fp16_stream) TRY(launch_layernorm(nullptr, w.x16r, b.ln2_g, b.ln2_b, MA_LN_EPS, M, EW, nullptr, w.ln16, st));
   else TRY(launch_layernorm(w.x32, nullptr, b.ln2_g, b.ln2_b, MA_LN_EPS, M, EW, nullptr, w.ln16, st));
-  TRY(launch_linear((const __half*)b.fc_w, (const __half*)b.fc_b, w.ln16, EW, w.f16, 4 * EW, M, 4 * EW, EW, MA_EPI_GELU,
+  TRY(enc_linear((const __half*)b.fc_w, (const __half*)b.fc_b, w.ln16, EW, w.f16, 4 * EW, M, 4 * EW, EW, MA_EPI_GELU,
                     st));
-  TRY(launch_linear((const __half*)b.proj_w, (const __half*)b.proj_b, w.f16, 4 * EW, w.y16, EW, M, EW, 4 * EW,
+  TRY(enc_linear((const __half*)b.proj_w, (const __half*)b.proj_b, w.f16, 4 * EW, w.y16, EW, M, EW, 4 * EW,
                     MA_EPI_NONE, st));
   TRY(launch_residual_add(fp16_stream ? nullptr : w.x32, w.x16r, w.y16, (long)M * EW, st));
   return 0;
@@ -101,34 +110,34 @@ static int encoder_chunk(const ma_encoder_weights* e, const __half* pc, int Bc, 
   const int R = Bc * NLAT;
   // a1/a2: Fourier features + normals -> input_proj (sal_perceiver.py:87-90)
   TRY(launch_fourier_embed(pc, P, w.data16, st));
-  TRY(launch_linear((const __half*)e->input_proj_w, (const __half*)e->input_proj_b, w.data16, 256, w.dproj16, EW, (int)P,
+  TRY(enc_linear((const __half*)e->input_proj_w, (const __half*)e->input_proj_b, w.data16, 256, w.dproj16, EW, (int)P,
                     EW, 256, MA_EPI_NONE, st));
   // a3: cross attention block (transformer_blocks.py:223-226): x = query
   TRY(launch_convert_rows(e->query, 0, EW, w.x32, 0, EW, R, EW, NLAT, st));
   TRY(launch_layernorm(w.x32, nullptr, e->ln1_g, e->ln1_b, MA_LN_EPS, R, EW, nullptr, w.ln16, st));
-  TRY(launch_linear((const __half*)e->cq_w, nullptr, w.ln16, EW, w.q16, EW, R, EW, EW, MA_EPI_NONE, st));
+  TRY(enc_linear((const __half*)e->cq_w, nullptr, w.ln16, EW, w.q16, EW, R, EW, EW, MA_EPI_NONE, st));
   TRY(launch_layernorm(nullptr, w.dproj16, e->ln2_g, e->ln2_b, MA_LN_EPS, (int)P, EW, nullptr, w.lnd16, st));
-  TRY(launch_linear((const __half*)e->ckv_w, nullptr, w.lnd16, EW, w.kv16, 2 * EW, (int)P, 2 * EW, EW, MA_EPI_NONE, st));
+  TRY(enc_linear((const __half*)e->ckv_w, nullptr, w.lnd16, EW, w.kv16, 2 * EW, (int)P, 2 * EW, EW, MA_EPI_NONE, st));
   // kv viewed [B,4096,12,128]: head h = columns 128h..: k | v  (transformer_blocks.py:171-173)
   TRY(launch_scatter_heads(w.kv16, 2 * EW, 0, 128, EH, NPTS, NPTS, w.kh, P, st));
   TRY(launch_scatter_heads(w.kv16, 2 * EW, 64, 128, EH, NPTS, NPTS, w.vh, P, st));
   TRY(launch_fill_i32(w.nkeys, NPTS, R, st));
   TRY(launch_attention(w.q16, EW, w.kh, w.vh, NPTS, EH, NLAT, nullptr, w.nkeys, NPTS, R, 0.125f, w.attn16, EW,
                        w.attn_scratch, st));
-  TRY(launch_linear((const __half*)e->cproj_w, (const __half*)e->cproj_b, w.attn16, EW, w.y16, EW, R, EW, EW,
+  TRY(enc_linear((const __half*)e->cproj_w, (const __half*)e->cproj_b, w.attn16, EW, w.y16, EW, R, EW, EW,
                     MA_EPI_NONE, st));
   TRY(launch_residual_add(w.x32, nullptr, w.y16, (long)R * EW, st));
   TRY(launch_layernorm(w.x32, nullptr, e->ln3_g, e->ln3_b, MA_LN_EPS, R, EW, nullptr, w.ln16, st));
-  TRY(launch_linear((const __half*)e->fc_w, (const __half*)e->fc_b, w.ln16, EW, w.f16, 4 * EW, R, 4 * EW, EW, MA_EPI_GELU,
+  TRY(enc_linear((const __half*)e->fc_w, (const __half*)e->fc_b, w.ln16, EW, w.f16, 4 * EW, R, 4 * EW, EW, MA_EPI_GELU,
                     st));
-  TRY(launch_linear((const __half*)e->proj_w, (const __half*)e->proj_b, w.f16, 4 * EW, w.y16, EW, R, EW, 4 * EW,
+  TRY(enc_linear((const __half*)e->proj_w, (const __half*)e->proj_b, w.f16, 4 * EW, w.y16, EW, R, EW, 4 * EW,
                     MA_EPI_NONE, st));
   TRY(launch_residual_add(w.x32, nullptr, w.y16, (long)R * EW, st));
   // a4: 8 self-attention blocks over the 257 latents, then ln_post -> point_feature (fp32)
   for (int i = 0; i < 8; i++) TRY(miche_block(e->enc[i], w, Bc, NLAT, false, st));
   TRY(launch_layernorm(w.x32, nullptr, e->lnpost_g, e->lnpost_b, MA_LN_EPS, R, EW, point_feature, w.ln16, st));
   // a8: prefix[:,0] = cond_head_proj(pf[:,0])   (row 0 of every shape: input rows are NLAT*EW apart)
-  TRY(launch_linear((const __half*)e->cond_head_w, (const __half*)e->cond_head_b, w.ln16, NLAT * EW, w.out16, 1024, Bc,
+  TRY(enc_linear((const __half*)e->cond_head_w, (const __half*)e->cond_head_b, w.ln16, NLAT * EW, w.out16, 1024, Bc,
                     1024, EW, MA_EPI_NONE, st));
   TRY(launch_convert_rows(w.out16, 1, 1024, prefix, 0, (long)NLAT * 1024, Bc, 1024, 0, st));
   // a7: to_shape_latents: pre_kl -> mean (first 64 channels) -> post_kl -> 16 blocks with an fp16 stream
@@ -136,16 +145,16 @@ static int encoder_chunk(const ma_encoder_weights* e, const __half* pc, int Bc, 
   for (int b = 0; b < Bc; b++)  // latent rows 1..256 of each shape, fp16, packed [256*Bc][768]
     TRY(launch_convert_rows(w.ln16 + ((size_t)b * NLAT + 1) * EW, 1, EW, w.cat16 + (size_t)b * 256 * 2 * EW, 1, 2 * EW,
                             256, EW, 0, st));
-  TRY(launch_linear((const __half*)e->pre_kl_w, (const __half*)e->pre_kl_b, w.cat16, 2 * EW, w.y16, 128, L, 128, EW,
+  TRY(enc_linear((const __half*)e->pre_kl_w, (const __half*)e->pre_kl_b, w.cat16, 2 * EW, w.y16, 128, L, 128, EW,
                     MA_EPI_NONE, st));
   cudaMemsetAsync(w.lat16, 0, (size_t)L * 256 * sizeof(__half), st);
   TRY(launch_convert_rows(w.y16, 1, 128, w.lat16, 1, 256, L, 64, 0, st));
-  TRY(launch_linear((const __half*)e->post_kl_w, (const __half*)e->post_kl_b, w.lat16, 256, w.x16r, EW, L, EW, 256,
+  TRY(enc_linear((const __half*)e->post_kl_w, (const __half*)e->post_kl_b, w.lat16, 256, w.x16r, EW, L, EW, 256,
                     MA_EPI_NONE, st));
   for (int i = 0; i < 16; i++) TRY(miche_block(e->dec[i], w, Bc, 256, true, st));
   // prefix[:,1:] = cond_proj(cat[pf[:,1:], shape_latents])   (meshanything.py:130)
   TRY(launch_convert_rows(w.x16r, 1, EW, w.cat16 + EW, 1, 2 * EW, L, EW, 0, st));
-  TRY(launch_linear((const __half*)e->cond_w, (const __half*)e->cond_b, w.cat16, 2 * EW, w.out16, 1024, L, 1024, 2 * EW,
+  TRY(enc_linear((const __half*)e->cond_w, (const __half*)e->cond_b, w.cat16, 2 * EW, w.out16, 1024, L, 1024, 2 * EW,
                     MA_EPI_NONE, st));
   for (int b = 0; b < Bc; b++)
     TRY(launch_convert_rows(w.out16 + (size_t)b * 256 * 1024, 1, 1024, prefix + ((size_t)b * NLAT + 1) * 1024, 0, 1024,
@@ -196,16 +205,16 @@ static int detok_chunk(const ma_tokenizer_weights* t, const int32_t* gen_ids, in
   const int S = NLAT + F, R = Bc * S, BF = Bc * F, BP = Bc * NLAT;
   // process_point_feature (meshanything.py:42-48)
   TRY(launch_convert_rows(point_feature, 0, EW, w.pfin16, 1, EW, BP, EW, 0, st));
-  TRY(launch_linear((const __half*)t->cond_w, (const __half*)t->cond_b, w.pfin16, EW, w.pf16, EW, BP, EW, EW, MA_EPI_NONE,
+  TRY(enc_linear((const __half*)t->cond_w, (const __half*)t->cond_b, w.pfin16, EW, w.pf16, EW, BP, EW, EW, MA_EPI_NONE,
                     st));
   // row 0 of every shape uses cond_head_proj instead
-  TRY(launch_linear((const __half*)t->cond_head_w, (const __half*)t->cond_head_b, w.pfin16, NLAT * EW, w.y16, EW, Bc, EW,
+  TRY(enc_linear((const __half*)t->cond_head_w, (const __half*)t->cond_head_b, w.pfin16, NLAT * EW, w.y16, EW, Bc, EW,
                     EW, MA_EPI_NONE, st));
   TRY(launch_convert_rows(w.y16, 1, EW, w.pf16, 1, (long)NLAT * EW, Bc, EW, 0, st));
   TRY(launch_add_table(w.pf16, nullptr, t->point_pe, NLAT, w.tmp32, BP, st));
   // faces (meshanything.py:54-60): codes -> project_down_codebook -> mask -> + pos_embedding -> LN
   TRY(launch_gather_codes(gen_ids, max_new, Bc, F, t->codebook, w.code16, w.mask, ids_out, st));
-  TRY(launch_linear((const __half*)t->down_w, (const __half*)t->down_b, w.code16, 3072, w.face16, EW, BF, EW, 3072,
+  TRY(enc_linear((const __half*)t->down_w, (const __half*)t->down_b, w.code16, 3072, w.face16, EW, BF, EW, 3072,
                     MA_EPI_NONE, st));
   TRY(launch_add_table(w.face16, w.mask, t->pos_embedding, F, w.tmp32 + (size_t)BP * EW, BF, st));
   // LayerNorms write straight into the concatenated [Bc][257+F][768] stream
@@ -218,24 +227,24 @@ static int detok_chunk(const ma_tokenizer_weights* t, const int32_t* gen_ids, in
   TRY(launch_fill_i32(w.nkeys, S, R, st));
   for (int i = 0; i < t->n_layers; i++) {  // BERT post-LN layer, no attention mask (meshanything.py:62-64)
     const ma_bert_layer& l = t->layer[i];
-    TRY(launch_linear((const __half*)l.in_w, (const __half*)l.in_b, w.x16, EW, w.qkv16, 3 * EW, R, 3 * EW, EW, MA_EPI_NONE,
+    TRY(enc_linear((const __half*)l.in_w, (const __half*)l.in_b, w.x16, EW, w.qkv16, 3 * EW, R, 3 * EW, EW, MA_EPI_NONE,
                       st));
     TRY(launch_scatter_heads(w.qkv16, 3 * EW, 0, 64, EH, 1, 1, w.qh, R, st));
     TRY(launch_scatter_heads(w.qkv16, 3 * EW, EW, 64, EH, S, S, w.kh, R, st));
     TRY(launch_scatter_heads(w.qkv16, 3 * EW, 2 * EW, 64, EH, S, S, w.vh, R, st));
     TRY(launch_attention(w.qh, EW, w.kh, w.vh, S, EH, S, nullptr, w.nkeys, S, R, 0.125f, w.attn16, EW, w.attn_scratch,
                          st));
-    TRY(launch_linear((const __half*)l.out_w, (const __half*)l.out_b, w.attn16, EW, w.y16, EW, R, EW, EW, MA_EPI_NONE, st));
+    TRY(enc_linear((const __half*)l.out_w, (const __half*)l.out_b, w.attn16, EW, w.y16, EW, R, EW, EW, MA_EPI_NONE, st));
     TRY(launch_layernorm(w.x32, w.y16, l.n1_g, l.n1_b, 1e-12f, R, EW, w.x32, w.x16, st));
-    TRY(launch_linear((const __half*)l.l1_w, (const __half*)l.l1_b, w.x16, EW, w.f16, 4 * EW, R, 4 * EW, EW, MA_EPI_GELU,
+    TRY(enc_linear((const __half*)l.l1_w, (const __half*)l.l1_b, w.x16, EW, w.f16, 4 * EW, R, 4 * EW, EW, MA_EPI_GELU,
                       st));
-    TRY(launch_linear((const __half*)l.l2_w, (const __half*)l.l2_b, w.f16, 4 * EW, w.y16, EW, R, EW, 4 * EW, MA_EPI_NONE,
+    TRY(enc_linear((const __half*)l.l2_w, (const __half*)l.l2_b, w.f16, 4 * EW, w.y16, EW, R, EW, 4 * EW, MA_EPI_NONE,
                       st));
     TRY(launch_layernorm(w.x32, w.y16, l.n2_g, l.n2_b, 1e-12f, R, EW, w.x32, w.x16, st));
   }
   // decoded[:, 257:] -> to_coor_logits -> argmax -> undiscretize (masked faces -> NaN)
   for (int b = 0; b < Bc; b++)
-    TRY(launch_linear((const __half*)t->coor_w, (const __half*)t->coor_b, w.x16 + ((size_t)b * S + NLAT) * EW, EW,
+    TRY(enc_linear((const __half*)t->coor_w, (const __half*)t->coor_b, w.x16 + ((size_t)b * S + NLAT) * EW, EW,
                       w.logits16 + (size_t)b * F * 1152, 1152, F, 1152, EW, MA_EPI_NONE, st));
   TRY(launch_coords(w.logits16, w.mask, out_xyz, BF, st));
   return 0;
@@ -246,6 +255,22 @@ static int detok_chunk(const ma_tokenizer_weights* t, const int32_t* gen_ids, in
 using namespace ma;
 
 extern "C" {
+
+int ma_set_tensor_cores(int enable) {
+  const int old = g_use_tc;
+  g_use_tc = enable ? 1 : 0;
+  return old;
+}
+
+int ma_linear_tc_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
+                     int epilogue, void* stream) {
+  if (!linear_tc_supported(M, N, K, ldx, ldy, x, W, y)) {
+    set_error("ma_linear_tc_f16: unsupported shape (M >= 64, N %% 128 == 0, K %% 64 == 0, 16-byte alignment)");
+    return 1;
+  }
+  return launch_linear_tc((const __half*)W, (const __half*)bias, (const __half*)x, ldx, (__half*)y, ldy, M, N, K, epilogue,
+                          (cudaStream_t)stream);
+}
 
 size_t ma_encoder_workspace_bytes(int B) { return carve_enc(nullptr, std::min(B, ENC_CHUNK)).total; }
 

@@ -32,6 +32,11 @@ bool check_launch(const char* what);
 int launch_linear(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
                   int K, int epi, cudaStream_t st);
 
+// gemm_tc.cu (tcgen05 + TMA; tolerance-checked stages only)
+bool linear_tc_supported(int M, int N, int K, int ldx, int ldy, const void* x, const void* W, const void* y);
+int launch_linear_tc(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
+                     int K, int epi, cudaStream_t st);
+
 // attention.cu
 size_t attention_scratch_bytes(int M, int H, int max_keys);
 int launch_attention(const __half* q, int ldq, const __half* K, const __half* V, long T, int H, int rows_per_slot,

@@ -85,3 +85,30 @@ def test_attention_bit_exact(H, T, nk):
         s = torch.einsum("hd,htd->ht", q[m].float(), k[:, :n].float()) * 0.125
         o = torch.einsum("ht,htd->hd", torch.softmax(s, -1), v[:, :n].float())
         assert (got[m].float() - o).abs().max() < 3e-3
+
+
+@gpu
+@pytest.mark.parametrize("M,N,K,epi", [(128, 128, 64, 0), (257, 768, 768, 0), (4096, 1536, 768, 0), (130, 128, 256, 1),
+                                        (1057, 3072, 768, 2), (300, 768, 3072, 0), (64, 1152, 768, 0)])
+def test_linear_tensor_core(M, N, K, epi):
+    """tcgen05/TMA GEMM (encoder / detokenizer): fp16 in, fp32 accumulate in the hardware's order -> compared with an
+    fp64 product rounded once to fp16 (tolerance: one fp16 ulp + fp32 accumulation noise) and with the canonical kernel."""
+    from meshanything_b200 import capi
+    g = torch.Generator().manual_seed(M + N + K)
+    w = (torch.randn(N, K, generator=g) * 0.05).half()
+    b = (torch.randn(N, generator=g) * 0.1).half()
+    x = torch.randn(M, K, generator=g).half()
+    d = _dev()
+    got = capi.linear_tc_f16(w.to(d), b.to(d), x.to(d), epilogue=epi).cpu()
+    canon = capi.linear_f16(w.to(d), b.to(d), x.to(d), epilogue=epi).cpu()
+    pre = x.double() @ w.double().T + b.double()
+    if epi == 1:
+        pre = torch.relu(pre)
+    elif epi == 2:
+        pre = torch.nn.functional.gelu(pre.half().double())
+    tol = 2.0 ** -10 * pre.abs() + 2e-3
+    assert ((got.double() - pre).abs() <= tol).all(), (got.double() - pre).abs().max()
+    # same values as the canonical kernel up to the last fp16 bit in a small fraction of the entries
+    diff = (got.float() - canon.float()).abs()
+    assert (diff <= 2.0 ** -9 * canon.float().abs() + 1e-3).all()
+    assert (diff == 0).float().mean() > 0.98
