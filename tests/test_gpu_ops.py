@@ -88,7 +88,7 @@ def test_attention_bit_exact(H, T, nk):
 
 
 @gpu
-@pytest.mark.parametrize("M,N,K,epi", [(128, 128, 64, 0), (257, 768, 768, 0), (4096, 1536, 768, 0), (130, 128, 256, 1),
+@pytest.mark.parametrize("M,N,K,epi", [(128, 128, 256, 0), (257, 768, 768, 0), (4096, 1536, 768, 0), (130, 128, 256, 1),
                                         (1057, 3072, 768, 2), (300, 768, 3072, 0), (64, 1152, 768, 0)])
 def test_linear_tensor_core(M, N, K, epi):
     """tcgen05/TMA GEMM (encoder / detokenizer): fp16 in, fp32 accumulate in the hardware's order -> compared with an
