@@ -121,3 +121,33 @@ def test_forward_drop_in(full):
     assert torch.equal(torch.nan_to_num(out1[0]), torch.nan_to_num(out[0]))
     outs = model(pc, sampling=True)
     assert outs.shape == out.shape
+
+
+@gpu
+def test_main_cli_writes_obj(tmp_path):
+    """`python main.py --input_type pc_normal --input_path x.npy ...` (reference flags, main.py:60-89) writes <uid>_gen.obj."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pc = synthetic_pc_normal(1, first=7)[0].numpy().astype(np.float16)
+    extra = np.concatenate([pc, pc[:100]], axis=0)            # > 4096 points: exercises the np.random.choice subsample
+    npy = tmp_path / "shape7.npy"
+    np.save(npy, extra)
+    out_dir = tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(root, "main.py"), "--input_type", "pc_normal", "--input_path", str(npy),
+                        "--out_dir", str(out_dir), "--pretrained_weights", "synthetic", "--n_max_triangles", "6",
+                        "--seed", "0"], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    objs = [os.path.join(dp, f) for dp, _, fs in os.walk(out_dir) for f in fs if f.endswith("_gen.obj")]
+    assert len(objs) == 1 and os.path.basename(objs[0]) == "shape7_gen.obj"
+    txt = open(objs[0]).read()
+    assert txt.count("\nf ") + txt.startswith("f ") >= 1 and "v " in txt
+    # the reference's input assertions (main.py:24,54)
+    bad = tmp_path / "bad.npy"
+    np.save(bad, pc[:1000])
+    r2 = subprocess.run([sys.executable, os.path.join(root, "main.py"), "--input_type", "pc_normal", "--input_path", str(bad),
+                         "--out_dir", str(out_dir), "--pretrained_weights", "synthetic", "--n_max_triangles", "6"],
+                        cwd=root, capture_output=True, text=True, timeout=600)
+    assert r2.returncode != 0 and "at least 4096 points" in r2.stderr

@@ -47,6 +47,8 @@ def full(path, title):
 
 launches(f"gpurun_out/launches_{tag}.csv")
 full(f"gpurun_out/prof_mega_{tag}.ncu-rep", "Persistent decode kernel")
+full(f"gpurun_out/prof_gemm_tc_{tag}.ncu-rep", "tcgen05 + TMA GEMM of the encoder (batch 8: M = 2056 / 32768 rows)")
+full(f"gpurun_out/prof_batched_{tag}.ncu-rep", "Canonical CUDA-core GEMM and attention kernels (batch 8 decode / prefill)")
 os.makedirs("profiles", exist_ok=True)
 open(f"profiles/ncu_summary_{tag}.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:3000])
