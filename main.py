@@ -20,24 +20,33 @@ from MeshAnything.models.meshanything import MeshAnything
 from mesh_to_pc import load_mesh, process_mesh_to_pc
 
 
+def _subsample_points(path, n_points=4096):
+    """`--input_type pc_normal`: an .npy of >= 4096 (xyz, normal) rows; a random 4096-subset without replacement
+    (global numpy RNG, seeded by --seed as the reference does through accelerate.set_seed)."""
+    cloud = np.load(path)
+    assert cloud.shape[0] >= n_points, "input pc_normal should have at least 4096 points"
+    keep = np.random.choice(cloud.shape[0], n_points, replace=False)
+    return cloud[keep]
+
+
+def _uid_of(path):
+    return path.split('/')[-1].split('.')[0]
+
+
 class Dataset:
+    """Same contract as the reference's Dataset (main.py:15-58): items are {'pc_normal': fp16 (4096, 6), 'uid': str},
+    coordinates centred on the bounding box and scaled to max |x| = 0.9995, unit normals asserted."""
+
     def __init__(self, input_type, input_list, mc=False):
-        super().__init__()
-        self.data = []
         if input_type == 'pc_normal':
-            for input_path in input_list:
-                cur_data = np.load(input_path)
-                assert cur_data.shape[0] >= 4096, "input pc_normal should have at least 4096 points"
-                idx = np.random.choice(cur_data.shape[0], 4096, replace=False)
-                cur_data = cur_data[idx]
-                self.data.append({'pc_normal': cur_data, 'uid': input_path.split('/')[-1].split('.')[0]})
+            clouds = [_subsample_points(p) for p in input_list]
         elif input_type == 'mesh':
-            mesh_list = [load_mesh(p) for p in input_list]
             if mc:
                 print("First Marching Cubes and then sample point cloud, need several minutes...")
-            pc_list, _ = process_mesh_to_pc(mesh_list, marching_cubes=mc)
-            for input_path, cur_data in zip(input_list, pc_list):
-                self.data.append({'pc_normal': cur_data, 'uid': input_path.split('/')[-1].split('.')[0]})
+            clouds, _ = process_mesh_to_pc([load_mesh(p) for p in input_list], marching_cubes=mc)
+        else:
+            raise ValueError(f"unknown input_type {input_type!r}")
+        self.data = [{'pc_normal': c, 'uid': _uid_of(p)} for c, p in zip(clouds, input_list)]
         print(f"dataset total data samples: {len(self.data)}")
 
     def __len__(self):
@@ -45,25 +54,26 @@ class Dataset:
 
     def __getitem__(self, idx):
         from meshanything_b200.inputs import normalize_pc_normal
-        return {'pc_normal': normalize_pc_normal(self.data[idx]['pc_normal']), 'uid': self.data[idx]['uid']}
+        entry = self.data[idx]
+        return {'pc_normal': normalize_pc_normal(entry['pc_normal']), 'uid': entry['uid']}
+
+
+_FLAGS = [  # (flag, default, type) -- the reference's command line (main.py:60-89)
+    ('--llm', "facebook/opt-350m", str), ('--input_dir', None, str), ('--input_path', None, str),
+    ('--out_dir', "inference_out", str), ('--pretrained_weights', "MeshAnything_350m.pth", str),
+    ('--codebook_size', 8192, int), ('--codebook_dim', 1024, int), ('--n_max_triangles', 800, int),
+    ('--batchsize_per_gpu', 1, int), ('--seed', 0, int),
+]
 
 
 def get_args():
     parser = argparse.ArgumentParser("MeshAnything", add_help=False)
-    parser.add_argument('--llm', default="facebook/opt-350m", type=str)
-    parser.add_argument('--input_dir', default=None, type=str)
-    parser.add_argument('--input_path', default=None, type=str)
-    parser.add_argument('--out_dir', default="inference_out", type=str)
-    parser.add_argument('--pretrained_weights', default="MeshAnything_350m.pth", type=str)
+    for flag, default, typ in _FLAGS:
+        parser.add_argument(flag, default=default, type=typ)
     parser.add_argument('--input_type', choices=['mesh', 'pc_normal'], default='pc',
                         help="Type of the asset to process (default: pc)")
-    parser.add_argument("--codebook_size", default=8192, type=int)
-    parser.add_argument("--codebook_dim", default=1024, type=int)
-    parser.add_argument("--n_max_triangles", default=800, type=int)
-    parser.add_argument("--batchsize_per_gpu", default=1, type=int)
-    parser.add_argument("--seed", default=0, type=int)
-    parser.add_argument("--mc", default=False, action="store_true")
-    parser.add_argument("--sampling", default=False, action="store_true")
+    for switch in ('--mc', '--sampling'):
+        parser.add_argument(switch, default=False, action="store_true")
     return parser.parse_args()
 
 

@@ -65,41 +65,38 @@ def load_mesh(path):
 
 
 def normalize_vertices(vertices, scale=0.9):
-    bbmin, bbmax = vertices.min(0), vertices.max(0)
-    center = (bbmin + bbmax) * 0.5
-    scale = 2.0 * scale / (bbmax - bbmin).max()
-    vertices = (vertices - center) * scale
-    return vertices, center, scale
+    """Centre on the bounding box and scale its longest side to 2*scale; returns (vertices, centre, factor)."""
+    lo, hi = vertices.min(0), vertices.max(0)
+    centre = 0.5 * (lo + hi)
+    factor = 2.0 * scale / (hi - lo).max()
+    return (vertices - centre) * factor, centre, factor
 
 
 def export_to_watertight(normalized_mesh, octree_depth: int = 7):
-    """mesh2sdf 128^3 SDF + marching cubes at level 2/size (reference mesh_to_pc.py:13-40)."""
+    """Watertight remesh used by `--mc` (reference mesh_to_pc.py:13-40): unsigned distance field on a 2^depth grid
+    (mesh2sdf), marching cubes at iso level 2/size, mapped back to the input frame."""
     try:
         import mesh2sdf.core
         import skimage.measure
     except Exception as e:  # pragma: no cover
         raise ImportError("--mc needs mesh2sdf, scikit-image and trimesh") from e
     size = 2 ** octree_depth
-    level = 2 / size
-    scaled_vertices, to_orig_center, to_orig_scale = normalize_vertices(normalized_mesh.vertices)
-    sdf = mesh2sdf.core.compute(scaled_vertices, normalized_mesh.faces, size=size)
-    vertices, faces, normals, _ = skimage.measure.marching_cubes(np.abs(sdf), level)
-    vertices = vertices / size * 2 - 1
-    vertices = vertices / to_orig_scale + to_orig_center
-    return trimesh.Trimesh(vertices, faces, normals=normals)
+    unit_vertices, centre, factor = normalize_vertices(normalized_mesh.vertices)
+    field = np.abs(mesh2sdf.core.compute(unit_vertices, normalized_mesh.faces, size=size))
+    verts, faces, normals, _ = skimage.measure.marching_cubes(field, 2 / size)
+    verts = (verts / size * 2 - 1) / factor + centre
+    return trimesh.Trimesh(verts, faces, normals=normals)
 
 
 def process_mesh_to_pc(mesh_list, marching_cubes=False, sample_num=4096):
-    pc_normal_list = []
-    return_mesh_list = []
+    """[mesh] -> ([fp16 (sample_num, 6) points + face normals], [mesh actually sampled])."""
+    clouds, used = [], []
     for mesh in mesh_list:
         if marching_cubes:
             mesh = export_to_watertight(mesh)
             print("MC over!")
-        return_mesh_list.append(mesh)
-        points, face_idx = mesh.sample(sample_num, return_index=True)
-        normals = mesh.face_normals[face_idx]
-        pc_normal = np.concatenate([points, normals], axis=-1, dtype=np.float16)
-        pc_normal_list.append(pc_normal)
+        pts, tri = mesh.sample(sample_num, return_index=True)
+        clouds.append(np.concatenate([pts, mesh.face_normals[tri]], axis=-1, dtype=np.float16))
+        used.append(mesh)
         print("process mesh success")
-    return pc_normal_list, return_mesh_list
+    return clouds, used
