@@ -1,7 +1,8 @@
 """Repeats full-length batch-1 generates with the persistent kernel, checking the poll-timeout flag, the time of every
 run and that all runs produce identical ids (python tools/stress_mega.py [runs] [faces])."""
 import sys, time, torch
-sys.path.insert(0, '.')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from meshanything_b200 import capi
 from meshanything_b200.checkpoint import decoder_specs, make_state_dict
 from meshanything_b200.decoder import DecoderArena, Generator

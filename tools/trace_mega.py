@@ -1,6 +1,7 @@
-"""Phase timeline of the persistent decode kernel (CTA 0, globaltimer): python tools_trace.py [new_tokens]"""
+"""Phase timeline of the persistent decode kernel (CTA 0, globaltimer): python tools/trace_mega.py [new_tokens]"""
 import sys, torch, collections
-sys.path.insert(0, '.')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from meshanything_b200 import capi
 from meshanything_b200.checkpoint import decoder_specs, make_state_dict
 from meshanything_b200.decoder import DecoderArena, Generator
