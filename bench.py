@@ -268,6 +268,10 @@ def main():
     t_prefill_ms = t100 - (n_lo - 1) * us_step_short / 1000.0
     dec_ms = ms / args.steps - max(0.0, t_prefill_ms)             # decode-loop part of one generate
     achieved = alg_bytes_per_gen / (dec_ms / 1000.0) / 1e9
+    traffic = None   # DRAM bytes per decode token from the committed ncu --set full capture of the same kernel
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if B == 1 and not args.sampling and os.path.exists(tpath):
+        traffic = json.load(open(tpath))["traffic_bytes_per_token"]
     roofline = {
         "bound": "hbm",
         "kernel": ("decode_mega_kernel (persistent: all 121 phases of a token, 512 tokens per launch)"
@@ -275,7 +279,7 @@ def main():
                    "decode step = 97 fast_gemv_kernel + 24 attention_kernel launches (one CUDA graph)" if B == 1 else
                    "decode step (gemm_canon + attention kernels, one CUDA graph)"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-        "traffic": None,
+        "traffic": traffic,
         "algorithmic_bytes_per_launch": alg_bytes_per_gen / n_dec,
         "launch": "one decode step (one token of every sequence); bytes = fp16 weights %d + KV read/write averaged over the run" % wbytes,
         "us_per_step_avg": dec_ms * 1000.0 / n_dec,
