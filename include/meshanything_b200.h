@@ -92,6 +92,14 @@ typedef struct {
   uint64_t seed;
 } ma_sampling;
 
+/* One pick of HF's sampling chain on its own (test surface; ma_decode_generate runs the same kernel per step):
+ * logits fp16 [B][vocab] -> out_tokens int32 [B].  do_sample = 0: argmax.  Otherwise TopKLogitsWarper(top_k)
+ * (every logit >= the k-th largest value survives, ties included) then TopPLogitsWarper(top_p), then one
+ * Philox(seed, row, step) uniform through the inverse CDF.  out_support int32 [B][256] (optional): the ids that
+ * survived both warpers, by descending logit, -1 padded.  1 <= top_k <= 128. */
+int ma_sample_tokens(const void* logits, int B, int vocab, const ma_sampling* sampling, int32_t* out_tokens,
+                     int32_t* out_support, void* stream);
+
 size_t ma_kv_cache_bytes(int n_layers, int B, int tmax);
 size_t ma_decoder_workspace_bytes(int B, int tmax);
 

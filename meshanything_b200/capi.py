@@ -39,7 +39,7 @@ EXPORTS = [
     "ma_abi_version", "ma_last_error", "ma_launch_count", "ma_linear_f16", "ma_layernorm",
     "ma_attention_scratch_bytes", "ma_attention_f16", "ma_kv_cache_bytes", "ma_decoder_workspace_bytes",
     "ma_decode_generate", "ma_decoder_debug", "ma_encoder_workspace_bytes", "ma_encoder_forward",
-    "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores",
+    "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores", "ma_sample_tokens",
 ]
 
 
@@ -71,6 +71,7 @@ def lib():
     L.ma_decoder_workspace_bytes.restype = C.c_size_t
     L.ma_decode_generate.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.POINTER(Sampling),
                                      C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]
+    L.ma_sample_tokens.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(Sampling), _vp, _vp, _vp]
     L.ma_decoder_debug.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int]
     L.ma_encoder_workspace_bytes.argtypes = [C.c_int]
     L.ma_encoder_workspace_bytes.restype = C.c_size_t
@@ -131,6 +132,20 @@ def linear_tc_f16(w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor
     check(lib().ma_linear_tc_f16(ptr(w), ptr(bias), ptr(x), x.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
                                  stream_ptr()), "ma_linear_tc_f16")
     return out
+
+
+def sample_tokens(logits: torch.Tensor, do_sample: bool = True, top_k: int = 50, top_p: float = 0.95, seed: int = 0,
+                  want_support: bool = False):
+    """One pick of the sampling chain (TopK -> TopP -> multinomial) over fp16 logits [B, vocab]."""
+    _need_cuda(logits)
+    assert logits.dtype == torch.float16 and logits.is_contiguous()
+    B, vocab = logits.shape
+    tok = torch.empty((B,), dtype=torch.int32, device=logits.device)
+    sup = torch.empty((B, 256), dtype=torch.int32, device=logits.device) if want_support else None
+    s = Sampling(int(do_sample), int(top_k), float(top_p), int(seed))
+    check(lib().ma_sample_tokens(ptr(logits), B, vocab, C.byref(s), ptr(tok), ptr(sup), stream_ptr()),
+          "ma_sample_tokens")
+    return (tok, sup) if want_support else tok
 
 
 def layernorm(x: Optional[torch.Tensor], res16: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,

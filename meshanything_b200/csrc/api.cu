@@ -175,6 +175,23 @@ int ma_attention_f16(const void* q, int ldq, const void* K, const void* V, long 
                           scale, (__half*)out, ldo, scratch, (cudaStream_t)stream);
 }
 
+int ma_sample_tokens(const void* logits, int B, int vocab, const ma_sampling* sampling, int32_t* out_tokens,
+                     int32_t* out_support, void* stream) {
+  if (!logits || !out_tokens || B < 1 || vocab < 1) {
+    set_error("ma_sample_tokens: bad arguments");
+    return 1;
+  }
+  SampleArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.logits = (const __half*)logits; sa.vocab = vocab; sa.B = B; sa.max_new = 1; sa.eos_id = -1; sa.pad_id = -1;
+  sa.do_sample = sampling ? sampling->do_sample : 0;
+  sa.top_k = sampling ? sampling->top_k : 0;
+  sa.top_p = sampling ? sampling->top_p : 1.0f;
+  sa.seed = sampling ? sampling->seed : 0;
+  sa.first = 1; sa.token_out = out_tokens; sa.support_out = out_support;
+  return launch_sample(sa, (cudaStream_t)stream);
+}
+
 size_t ma_kv_cache_bytes(int n_layers, int B, int tmax) {
   return (size_t)n_layers * 2 * B * NHEAD * (size_t)tmax * HD * sizeof(__half);
 }

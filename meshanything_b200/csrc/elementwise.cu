@@ -200,19 +200,29 @@ __device__ float philox_uniform(unsigned long long seed, uint32_t row, uint32_t 
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
 constexpr int SAMPLE_THREADS = 256;
-constexpr int TOPK_MAX = 64;
+constexpr int KEEP_MAX = 256;  // capacity of the kept set (top_k plus ties at the threshold)
 
-// One CTA per row.  Greedy: argmax of the fp16 logits (HF 4.39.3 _greedy_search keeps fp16).
-// Sampling (HF _sample with TopKLogitsWarper(50) then TopPLogitsWarper(0.95), logits_process.py):
-//   keep logits >= the k-th largest; softmax over the kept set; drop the smallest-probability tokens
-//   whose cumulative probability (ascending order) is <= 1 - top_p, always keeping the largest;
-//   renormalise; inverse-CDF draw with a Philox uniform (descending order, ties by lower index).
+// order-preserving 16-bit key of an fp16 value: larger value <=> larger key (-0 < +0, irrelevant here)
+__device__ __forceinline__ unsigned key16(__half h) {
+  const unsigned u = __half_as_ushort(h);
+  return (u & 0x8000u) ? (~u & 0xffffu) : (u | 0x8000u);
+}
+
+// One CTA per row.  Greedy: argmax of the fp16 logits (HF 4.39.3 _greedy_search keeps fp16), lowest index on ties.
+// Sampling = HF _sample with TopKLogitsWarper(top_k) then TopPLogitsWarper(top_p) (logits_process.py):
+//   1. keep every logit >= the k-th largest VALUE (ties at the threshold are kept, as `scores < kth` removes
+//      only strictly smaller ones): exact k-th value by a two-level radix select on the 16-bit keys;
+//   2. softmax over the kept set; in ascending order drop tokens while the cumulative probability is <= 1 - top_p,
+//      always keeping the largest;
+//   3. inverse-CDF draw over the survivors (descending value, higher index first) with one Philox uniform.
 __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
   __shared__ float sv[SAMPLE_THREADS];
   __shared__ int si[SAMPLE_THREADS];
-  __shared__ float topv[TOPK_MAX];
-  __shared__ int topi[TOPK_MAX];
-  __shared__ int picked;
+  __shared__ int hist[256];
+  __shared__ float keepv[KEEP_MAX], sortv[KEEP_MAX];
+  __shared__ int keepi[KEEP_MAX], sorti[KEEP_MAX];
+  __shared__ int s_bin, s_above;
+  extern __shared__ unsigned short keys[];  // [vocab] order-preserving keys of the row (sampling only)
   const int b = blockIdx.x, tid = threadIdx.x;
   const __half* lg = a.logits + (long)b * a.vocab;
   const int gen = a.first ? 0 : a.s.gen[b];
@@ -222,15 +232,13 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
     for (int i = tid; i < a.vocab; i += SAMPLE_THREADS) dst[i] = lg[i];
   }
 
-  const int rounds = a.do_sample ? min(a.top_k, TOPK_MAX) : 1;
-  for (int k = 0; k < rounds; k++) {
+  int n_keep = 1;
+  if (!a.do_sample) {
     float bv = -INFINITY;
     int bi = 0x7fffffff;
     for (int i = tid; i < a.vocab; i += SAMPLE_THREADS) {
       const float v = __half2float(lg[i]);
-      bool taken = false;
-      for (int j = 0; j < k; j++) taken |= (topi[j] == i);
-      if (!taken && better(v, i, bv, bi)) { bv = v; bi = i; }
+      if (better(v, i, bv, bi)) { bv = v; bi = i; }
     }
     sv[tid] = bv; si[tid] = bi;
     __syncthreads();
@@ -238,70 +246,160 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
       if (tid < s && better(sv[tid + s], si[tid + s], sv[tid], si[tid])) { sv[tid] = sv[tid + s]; si[tid] = si[tid + s]; }
       __syncthreads();
     }
-    if (tid == 0) { topv[k] = sv[0]; topi[k] = si[0]; }
+    if (tid == 0) { sortv[0] = sv[0]; sorti[0] = si[0]; }
+    __syncthreads();
+  } else {
+    const int k = min(a.top_k, a.vocab);
+    // stage the row's keys once (coalesced); every later pass reads shared memory
+    for (int i = tid; i < a.vocab; i += SAMPLE_THREADS) keys[i] = (unsigned short)key16(lg[i]);
+    // ---- level 1: histogram of the high byte
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < a.vocab; i += SAMPLE_THREADS) atomicAdd(&hist[keys[i] >> 8], 1);
+    __syncthreads();
+    if (tid == 0) {
+      int above = 0, bin = 255;
+      for (; bin > 0; bin--) {
+        if (above + hist[bin] >= k) break;
+        above += hist[bin];
+      }
+      s_bin = bin; s_above = above;
+    }
+    __syncthreads();
+    const int b1 = s_bin, above1 = s_above;
+    // ---- level 2: low byte inside that bin
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < a.vocab; i += SAMPLE_THREADS) {
+      const unsigned kk = keys[i];
+      if ((int)(kk >> 8) == b1) atomicAdd(&hist[kk & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int above = above1, bin = 255;
+      for (; bin > 0; bin--) {
+        if (above + hist[bin] >= k) break;
+        above += hist[bin];
+      }
+      s_bin = (b1 << 8) | bin;   // key of the k-th largest value
+    }
+    __syncthreads();
+    const unsigned kth = (unsigned)s_bin;
+    // ---- ordered compaction (deterministic): strictly greater first, then the ties at the threshold by index.
+    // Thread t owns the contiguous ids [t*per, (t+1)*per); block-wide exclusive scans give the slots.
+    const int per = (a.vocab + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+    const int lo = tid * per, hi = min(a.vocab, lo + per);
+    int ngt = 0, neq = 0;
+    for (int i = lo; i < hi; i++) {
+      const unsigned kk = keys[i];
+      ngt += kk > kth;
+      neq += kk == kth;
+    }
+    si[tid] = ngt; hist[tid] = neq;
+    __syncthreads();
+    for (int d = 1; d < SAMPLE_THREADS; d <<= 1) {
+      const int x = tid >= d ? si[tid - d] : 0, y = tid >= d ? hist[tid - d] : 0;
+      __syncthreads();
+      si[tid] += x; hist[tid] += y;
+      __syncthreads();
+    }
+    const int tot_gt = si[SAMPLE_THREADS - 1], tot_eq = hist[SAMPLE_THREADS - 1];
+    int sg = si[tid] - ngt, se = tot_gt + hist[tid] - neq;
+    for (int i = lo; i < hi; i++) {
+      const unsigned kk = keys[i];
+      if (kk > kth) { keepv[sg] = __half2float(lg[i]); keepi[sg] = i; sg++; }
+      else if (kk == kth) {
+        if (se < KEEP_MAX) { keepv[se] = __half2float(lg[i]); keepi[se] = i; }
+        se++;
+      }
+    }
+    __syncthreads();
+    n_keep = min(tot_gt + tot_eq, KEEP_MAX);  // > KEEP_MAX only if > 128 logits tie at the threshold: lowest ids kept
+    // ---- rank sort: descending value, ties by descending index.  TopPLogitsWarper removes a prefix of an
+    // (unstable) ascending torch.sort, so WHICH of several equal logits it drops is undefined in the reference;
+    // here the lowest ids among equals go first.  The number kept and every non-tied member are HF's.
+    if (tid < n_keep) {
+      const float v = keepv[tid];
+      const int ix = keepi[tid];
+      int rank = 0;
+      for (int j = 0; j < n_keep; j++) rank += (keepv[j] > v || (keepv[j] == v && keepi[j] > ix)) ? 1 : 0;
+      sortv[rank] = v; sorti[rank] = ix;
+    }
+    __syncthreads();
+  }
+
+  if (a.support_out) {  // test hook: the kept set after top-k / top-p is written below by thread 0
+    for (int i = tid; i < KEEP_MAX; i += SAMPLE_THREADS) a.support_out[(long)b * KEEP_MAX + i] = -1;
     __syncthreads();
   }
 
   if (tid == 0) {
-    int tok = topi[0];
+    int tok = sorti[0];
     if (a.do_sample) {
-      const int K = rounds;
+      const int K = n_keep;
       // softmax over the kept set (descending order), fp32
-      float p[TOPK_MAX], sum = 0.0f;
-      for (int j = 0; j < K; j++) { p[j] = ma_exp(fsub(topv[j], topv[0])); sum = fadd(sum, p[j]); }
-      for (int j = 0; j < K; j++) p[j] = __fdiv_rn(p[j], sum);
+      float sum = 0.0f;
+      for (int j = 0; j < K; j++) { keepv[j] = ma_exp(fsub(sortv[j], sortv[0])); sum = fadd(sum, keepv[j]); }
+      for (int j = 0; j < K; j++) keepv[j] = __fdiv_rn(keepv[j], sum);
       // top-p: ascending cumulative probability <= 1 - top_p is removed (keep >= 1 token)
       int keep = K;
       float cum = 0.0f;
       const float thr = fsub(1.0f, a.top_p);
       for (int j = K - 1; j >= 1; j--) {
-        cum = fadd(cum, p[j]);
+        cum = fadd(cum, keepv[j]);
         if (cum <= thr) keep = j; else break;
       }
+      if (a.support_out)
+        for (int j = 0; j < keep; j++) a.support_out[(long)b * KEEP_MAX + j] = sorti[j];
       float ksum = 0.0f;
-      for (int j = 0; j < keep; j++) ksum = fadd(ksum, p[j]);
+      for (int j = 0; j < keep; j++) ksum = fadd(ksum, keepv[j]);
       const float u = fmul(philox_uniform(a.seed, (uint32_t)b, (uint32_t)gen), ksum);
       float acc = 0.0f;
-      tok = topi[keep - 1];
+      tok = sorti[keep - 1];
       for (int j = 0; j < keep; j++) {
-        acc = fadd(acc, p[j]);
-        if (u < acc) { tok = topi[j]; break; }
+        acc = fadd(acc, keepv[j]);
+        if (u < acc) { tok = sorti[j]; break; }
       }
     }
     if (a.forced) tok = a.forced[(long)b * a.max_new + gen];
     int fin = a.first ? 0 : a.s.finished[b];
     if (fin) tok = a.pad_id;  // HF: next_tokens * unfinished + pad * (1 - unfinished)
-    if (gen < a.max_new) a.out_ids[(long)b * a.max_new + gen] = tok;
-    if (!fin && tok == a.eos_id) {
-      fin = 1;
-      a.s.lens[b] = gen + 1;
+    if (a.out_ids && gen < a.max_new) a.out_ids[(long)b * a.max_new + gen] = tok;
+    if (a.s.lens) {
+      if (!fin) a.s.lens[b] = gen + 1;
+      if (!fin && tok == a.eos_id) fin = 1;
+      a.s.finished[b] = fin;
+      a.s.tok[b] = tok;
+      a.s.gen[b] = gen + 1;
+      const int np = a.first ? PREFIX : a.s.pos[b] + 1;
+      a.s.pos[b] = np;
+      if (a.nkeys_next) a.nkeys_next[b] = np + 1;
     }
-    if (!fin) a.s.lens[b] = gen + 1;
-    a.s.finished[b] = fin;
-    a.s.tok[b] = tok;
-    a.s.gen[b] = gen + 1;
-    const int np = a.first ? PREFIX : a.s.pos[b] + 1;
-    a.s.pos[b] = np;
-    if (a.nkeys_next) a.nkeys_next[b] = np + 1;
-    picked = fin;
+    if (a.token_out) a.token_out[b] = tok;
+    si[0] = fin;
   }
   __syncthreads();
   // all_done: every row finished.  Rows are handled by different CTAs: each clears the flag if unfinished.
-  if (tid == 0 && a.all_done && !picked) *a.all_done = 0;
+  if (tid == 0 && a.all_done && !si[0]) *a.all_done = 0;
 }
 
 __global__ void set_flag_kernel(int* f, int v) { *f = v; }
 
 int launch_sample(const SampleArgs& a, cudaStream_t st) {
-  if (a.do_sample && (a.top_k < 1)) {
-    set_error("sampling needs top_k >= 1");
+  if (a.do_sample && (a.top_k < 1 || a.top_k > KEEP_MAX / 2)) {
+    set_error("sampling needs 1 <= top_k <= %d", KEEP_MAX / 2);
     return 1;
   }
   if (a.all_done) {
     set_flag_kernel<<<1, 1, 0, st>>>(a.all_done, 1);
     count_launch();
   }
-  sample_kernel<<<a.B, SAMPLE_THREADS, 0, st>>>(a);
+  const size_t dyn = a.do_sample ? (size_t)a.vocab * sizeof(unsigned short) : 0;
+  if (dyn > 32 * 1024) {
+    set_error("sampling supports vocab <= 16384 (got %d)", a.vocab);
+    return 1;
+  }
+  sample_kernel<<<a.B, SAMPLE_THREADS, dyn, st>>>(a);
   count_launch();
   return check_launch("sample_kernel") ? 0 : 1;
 }

@@ -66,6 +66,8 @@ struct SampleArgs {
   __half* logits_out;    // [max_new][B][vocab] or null
   int* all_done;         // device flag: 1 when every row finished
   int* nkeys_next;       // optional [B]: keys visible to the next step (pos + 1), for the batch-1 fast path
+  int32_t* support_out;  // test hook [B][256]: token ids that survive top-k/top-p (descending), -1 padded
+  int32_t* token_out;    // test hook [B]: the picked token
 };
 int launch_sample(const SampleArgs& a, cudaStream_t st);
 int launch_fill_i32(int32_t* p, int v, long n, cudaStream_t st);

@@ -112,3 +112,95 @@ def test_linear_tensor_core(M, N, K, epi):
     diff = (got.float() - canon.float()).abs()
     assert (diff <= 2.0 ** -9 * canon.float().abs() + 1e-3).all()
     assert (diff == 0).float().mean() > 0.98
+
+
+def _hf_support(row: torch.Tensor, top_k: int, top_p: float):
+    """Support after transformers' own TopKLogitsWarper -> TopPLogitsWarper (the chain HF _sample builds for
+    meshanything.py:150-158), evaluated in fp32 on the CPU.  Returns (ids by descending logit, near_boundary)."""
+    from transformers.generation.logits_process import TopKLogitsWarper, TopPLogitsWarper
+    s = row.float()[None]
+    s = TopKLogitsWarper(top_k)(None, s)
+    after_k = s.clone()
+    if top_p < 1.0:  # generation/utils.py adds the top-p warper only below 1.0
+        s = TopPLogitsWarper(top_p)(None, s)
+    keep = torch.nonzero(torch.isfinite(s[0]))[:, 0]
+    order = sorted(keep.tolist(), key=lambda i: (-float(row[i]), -i))  # reverse of torch's stable ascending sort
+    # rows whose ascending cumulative probability passes within 1e-5 of 1 - top_p can flip with summation order
+    cum = torch.sort(after_k[0].double()).values.softmax(-1).cumsum(-1)
+    near = top_p < 1.0 and bool(((cum - (1 - top_p)).abs() < 1e-5).any())
+    return order, near
+
+
+@gpu
+@pytest.mark.parametrize("top_k,top_p", [(50, 0.95), (50, 1.0), (1, 0.95), (128, 0.5), (7, 0.9)])
+def test_sampler_support_matches_hf_warpers(top_k, top_p):
+    """ma_sample_tokens keeps exactly the tokens HF's warpers keep — including every tie at the k-th value
+    (fp16 logits over 8195 ids tie often) — and draws inside that set."""
+    from meshanything_b200 import capi
+    g = torch.Generator().manual_seed(top_k)
+    B, V = 48, 8195
+    lg = (torch.randn(B, V, generator=g) * 2.0).half()
+    lg[1] = (torch.randn(V, generator=g) * 0.01).half()                  # nearly flat: top-p removes nothing much
+    lg[2] = torch.round(torch.randn(V, generator=g) * 2).half()          # heavy ties (integers)
+    lg[3] = 0                                                            # everything ties
+    lg[3, 77] = 1.0
+    lg[4, :] = -3.0
+    lg[4, 5:60] = 2.5                                                    # 55 ties at the threshold for k = 50
+    lg[5] = (torch.randn(V, generator=g) * 30).half()                    # peaked: one token takes the mass
+    lg[6] = -lg[0].abs()                                                 # all non-positive
+    tok, sup = capi.sample_tokens(lg.to(_dev()), True, top_k, top_p, seed=3, want_support=True)
+    tok, sup = tok.cpu(), sup.cpu()
+    checked = 0
+    for r in range(B):
+        got = [int(v) for v in sup[r] if v >= 0]
+        if lg[r].float().ge(torch.topk(lg[r].float(), top_k).values[-1]).sum() > 256:
+            continue  # more ties than the kernel's kept-set capacity (row 3): covered below
+        want, near = _hf_support(lg[r], top_k, top_p)
+        if near:
+            continue
+        # torch.sort inside TopPLogitsWarper is unstable: which of several EQUAL logits at the top-p boundary
+        # survive is undefined in the reference.  Everything else must be identical: the count, the kept
+        # values, and every member above the boundary value.
+        assert len(got) == len(want), r
+        assert [float(lg[r, i]) for i in got] == [float(lg[r, i]) for i in want], r
+        edge = float(lg[r, want[-1]])
+        assert [i for i in got if float(lg[r, i]) > edge] == [i for i in want if float(lg[r, i]) > edge], r
+        n_edge_all = int((lg[r].float() == edge).sum())
+        if n_edge_all == sum(1 for i in want if float(lg[r, i]) == edge):
+            assert got == want, r                      # no tie was cut: full identity
+        assert int(tok[r]) in got
+        checked += 1
+    assert checked >= B - 6
+    # same seed -> same draw; another seed -> another draw somewhere
+    tok2 = capi.sample_tokens(lg.to(_dev()), True, top_k, top_p, seed=3).cpu()
+    assert torch.equal(tok, tok2)
+    if top_k > 1:
+        tok3 = capi.sample_tokens(lg.to(_dev()), True, top_k, top_p, seed=4).cpu()
+        assert not torch.equal(tok, tok3)
+    # greedy = lowest index among the maxima
+    am = capi.sample_tokens(lg.to(_dev()), False).cpu()
+    for r in range(B):
+        m = lg[r].float().max()
+        assert int(am[r]) == int(torch.nonzero(lg[r].float() == m)[0, 0])
+
+
+@gpu
+def test_sampler_draw_frequencies():
+    """Every row has the same logits and its own Philox stream: empirical frequencies follow the renormalised
+    top-k/top-p softmax (5-sigma binomial band)."""
+    from meshanything_b200 import capi
+    g = torch.Generator().manual_seed(9)
+    V, B = 8195, 20000
+    row = (torch.randn(V, generator=g) * 1.5).half()
+    hf, _ = _hf_support(row, 50, 0.95)
+    tok, sup = capi.sample_tokens(row[None].repeat(B, 1).contiguous().to(_dev()), True, 50, 0.95, seed=11,
+                                  want_support=True)
+    tok = tok.cpu()
+    want = [int(v) for v in sup[0].cpu() if v >= 0]
+    assert row[want].tolist() == row[hf].tolist()   # same kept values as HF (equal logits at the edge are interchangeable)
+    p = torch.softmax(row[want].double(), -1)
+    counts = torch.bincount(tok.long(), minlength=V)
+    assert int(counts.sum()) == B and int(counts[want].sum()) == B
+    f = counts[want].double() / B
+    sigma = (p * (1 - p) / B).sqrt()
+    assert bool(((f - p).abs() < 5 * sigma + 1e-4).all())
