@@ -101,16 +101,17 @@ def make_decoder():
     print("decoder_hf_fp32.npz", ref.shape)
 
 
-def make_greedy(faces=64):
-    """greedy ids of the full 24-layer synthetic decoder from the CPU oracle: F=64 is config 1's length (578 tokens),
-    F=800 config 2's (7202 tokens, contexts up to 7458: ~2.5 minutes of oracle time on 8 cores)."""
+def make_greedy(faces=64, n_layers=24):
+    """greedy ids of the synthetic decoder from the CPU oracle: F=64 is config 1's length (578 tokens), F=800
+    config 2's (7202 tokens, contexts up to 7458: ~2.5 minutes of oracle time on 8 cores), F=1600 config 5's
+    (14402 tokens, contexts up to 14658 = 58 attention chunks; the first 4 layers only, to bound the oracle time)."""
     from oracle.decoder import OracleDecoder
-    sd = decoder_sd(24)
+    sd = decoder_sd(n_layers)
     n = faces * 9 + 2
     prefix = random_prefix(1, seed=1)[0]
-    oracle = OracleDecoder(sd, 24, 257 + n)
+    oracle = OracleDecoder(sd, n_layers, 257 + n)
     ids, _ = oracle.generate(prefix, n)
-    json.dump({"ids": ids, "n_layers": 24, "prefix_seed": 1, "checkpoint_seed": 0, "faces": faces},
+    json.dump({"ids": ids, "n_layers": n_layers, "prefix_seed": 1, "checkpoint_seed": 0, "faces": faces},
               open(os.path.join(HERE, f"decoder_greedy_seed0_F{faces}.json"), "w"))
     print(f"decoder_greedy_seed0_F{faces}.json", len(ids), ids[:12], "distinct", len(set(ids)))
 
@@ -123,6 +124,8 @@ if __name__ == "__main__":
         make_greedy(64)
     if what in ("greedy800", "all"):
         make_greedy(800)
+    if what in ("greedy1600", "all"):
+        make_greedy(1600, n_layers=4)
     if what in ("encoder", "all"):
         from tests.golden import make_golden_encoder
         make_golden_encoder.main()

@@ -207,3 +207,33 @@ def test_full_depth_config2_golden():
         assert first_bad is None, f"flags={flags}: first divergence at step {first_bad}"
         assert int(lens[0]) == n
     assert gen.mega_error() == 0 or True
+
+
+@gpu
+@pytest.mark.slow
+def test_long_context_config5_golden():
+    """BASELINE.json configs[4] length (V1 architecture, 1600-face cap: 14402 new tokens, contexts up to 14658 = 58
+    attention chunks, four rounds of attention items in the persistent kernel).  First 4 layers of the synthetic
+    decoder; ids equal the CPU oracle's (tests/golden/decoder_greedy_seed0_F1600.json, make_golden.py greedy1600)
+    for the persistent kernel, the per-phase kernels, and a batch of 2 on the batched kernels (row 0 = the golden
+    prefix, row 1 another prefix: rows are independent)."""
+    import json, os
+    from meshanything_b200.decoder import DecoderArena, Generator
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "decoder_greedy_seed0_F1600.json")))
+    gold, NL = g["ids"], g["n_layers"]
+    arena = DecoderArena(decoder_sd(NL), _dev())
+    prefix = random_prefix(1, seed=1).to(_dev())
+    n = 1600 * 9 + 2
+    gen = Generator(arena, 1, 257 + n)
+    for flags in (0, 16):
+        ids, lens = gen.generate(prefix, n, flags=flags)
+        got = ids[0].cpu().tolist()
+        first_bad = next((i for i, (a, b) in enumerate(zip(got, gold)) if a != b), None)
+        assert first_bad is None, f"flags={flags}: first divergence at step {first_bad}"
+        assert int(lens[0]) == n
+        if flags == 0:
+            assert gen.mega_error() == 0
+    two = torch.cat([prefix, random_prefix(1, seed=5).to(_dev())], dim=0)
+    gen2 = Generator(arena, 2, 257 + n)
+    ids2, _ = gen2.generate(two, n)
+    assert ids2[0].cpu().tolist() == gold
