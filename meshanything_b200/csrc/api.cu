@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "canon.cuh"
@@ -126,7 +127,20 @@ static cudaStream_t g_stream = nullptr;
 static int* g_flag_host = nullptr;  // pinned
 static cudaEvent_t g_ev_in = nullptr, g_ev_out = nullptr, g_ev_flag = nullptr;
 
+static int g_device = -1;   // the library keeps one internal stream + graph cache: one device per process
+static std::mutex g_mu;     // ma_decode_generate is serialised (graph cache, pinned flag, internal stream)
+
 static int ensure_globals() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("cudaGetDevice: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  if (g_device >= 0 && dev != g_device) {
+    set_error("ma_decode_generate was first used on device %d; this process now runs on device %d "
+              "(one process per GPU)", g_device, dev);
+    return 1;
+  }
   if (!g_stream) {
     if (cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc((void**)&g_flag_host, 64, cudaHostAllocDefault) != cudaSuccess ||
@@ -136,6 +150,7 @@ static int ensure_globals() {
       set_error("cannot create stream/events: %s", cudaGetErrorString(cudaGetLastError()));
       return 1;
     }
+    g_device = dev;
   }
   return 0;
 }
@@ -218,6 +233,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
     set_error("ma_decode_generate: sequence of %d exceeds %d learned positions", PREFIX + max_new, w->npos - 2);
     return 1;
   }
+  std::lock_guard<std::mutex> lock(g_mu);
   if (ensure_globals()) return 1;
   cudaStream_t user = (cudaStream_t)stream;
   cudaStream_t st = g_stream;  // graph capture is illegal on the legacy default stream: always run on our own

@@ -16,7 +16,7 @@ constexpr int GEMM_WARPS = 4;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int R, int T>
+template <int R, int T, bool PIPE>
 __global__ void __launch_bounds__(GEMM_WARPS * 32)
     gemm_canon_kernel(const __half* __restrict__ W, const __half* __restrict__ bias, const __half* __restrict__ x,
                       int ldx, __half* __restrict__ y, int ldy, int M, int N, int K, int epi) {
@@ -37,25 +37,58 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32)
 #pragma unroll
   for (int t = 0; t < T; t++) xoff[t] = (long)min(m0 + t, M - 1) * ldx + 8 * lane;
 
+  // Software pipeline over the 256-wide K groups: the raw 16-byte pieces of group g+1 are requested while group g
+  // is multiplied (x right after its conversion, each weight row right after its own conversion), so a warp hides
+  // its own load latency -- at small M there are fewer than two warps per scheduler to hide it otherwise.
   const int G = K >> 8;
-  for (int g = 0; g < G; g++) {
-    float xf[T][8];
+  if constexpr (PIPE) {
+    uint4 xr[T], wr[R];
 #pragma unroll
-    for (int t = 0; t < T; t++) {
-      uint4 u = *reinterpret_cast<const uint4*>(x + xoff[t] + 256 * g);
-      unpack8(u, xf[t]);
-    }
+    for (int t = 0; t < T; t++) xr[t] = *reinterpret_cast<const uint4*>(x + xoff[t]);
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-      uint4 u = ldg_nc16(W + woff[r] + 256 * g);
-      float wf[8];
-      unpack8(u, wf);
+    for (int r = 0; r < R; r++) wr[r] = ldg_nc16(W + woff[r]);
+    for (int g = 0; g < G; g++) {
+      const int gn = 256 * min(g + 1, G - 1);   // the last group re-requests itself (no branch, no out-of-range read)
+      float xf[T][8];
 #pragma unroll
       for (int t = 0; t < T; t++) {
-        float a = acc[r * T + t];
+        unpack8(xr[t], xf[t]);
+        xr[t] = *reinterpret_cast<const uint4*>(x + xoff[t] + gn);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; j++) a = ffma(wf[j], xf[t][j], a);
-        acc[r * T + t] = a;
+      for (int r = 0; r < R; r++) {
+        float wf[8];
+        unpack8(wr[r], wf);
+        wr[r] = ldg_nc16(W + woff[r] + gn);
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+          float a = acc[r * T + t];
+#pragma unroll
+          for (int j = 0; j < 8; j++) a = ffma(wf[j], xf[t][j], a);
+          acc[r * T + t] = a;
+        }
+      }
+    }
+  } else {
+    for (int g = 0; g < G; g++) {
+      float xf[T][8];
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        uint4 u = *reinterpret_cast<const uint4*>(x + xoff[t] + 256 * g);
+        unpack8(u, xf[t]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        uint4 u = ldg_nc16(W + woff[r] + 256 * g);
+        float wf[8];
+        unpack8(u, wf);
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+          float a = acc[r * T + t];
+#pragma unroll
+          for (int j = 0; j < 8; j++) a = ffma(wf[j], xf[t][j], a);
+          acc[r * T + t] = a;
+        }
       }
     }
   }
@@ -91,14 +124,18 @@ int launch_linear(const __half* W, const __half* bias, const __half* x, int ldx,
     set_error("ma_linear_f16: x/W must be 16-byte aligned and ldx a multiple of 8");
     return 1;
   }
+  // PIPE (254 registers, 2 CTAs/SM) wins while the grid is a few waves at most (B200, M = 16/64: fc2 -30 %, others
+  // +-5 %); at prefill sizes the 3-CTA/SM plain loop is 10 % faster (profiles/batched_kernels_r01.json)
+  const bool pipe = M <= 512;
   if (M <= 4) {
     constexpr int R = 8, T = 4;
     dim3 grid((M + T - 1) / T, (N + GEMM_WARPS * R - 1) / (GEMM_WARPS * R));
-    gemm_canon_kernel<R, T><<<grid, GEMM_WARPS * 32, 0, st>>>(W, bias, x, ldx, y, ldy, M, N, K, epi);
+    gemm_canon_kernel<R, T, true><<<grid, GEMM_WARPS * 32, 0, st>>>(W, bias, x, ldx, y, ldy, M, N, K, epi);
   } else {
     constexpr int R = 8, T = 8;
     dim3 grid((M + T - 1) / T, (N + GEMM_WARPS * R - 1) / (GEMM_WARPS * R));
-    gemm_canon_kernel<R, T><<<grid, GEMM_WARPS * 32, 0, st>>>(W, bias, x, ldx, y, ldy, M, N, K, epi);
+    if (pipe) gemm_canon_kernel<R, T, true><<<grid, GEMM_WARPS * 32, 0, st>>>(W, bias, x, ldx, y, ldy, M, N, K, epi);
+    else gemm_canon_kernel<R, T, false><<<grid, GEMM_WARPS * 32, 0, st>>>(W, bias, x, ldx, y, ldy, M, N, K, epi);
   }
   count_launch();
   return check_launch("gemm_canon_kernel") ? 0 : 1;

@@ -35,13 +35,14 @@ def timed(fn, n=20, warm=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--skip-attention", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     B, H, D = args.batch, 16, 64
     L = capi.lib()
     out = {"batch": B, "attention": [], "linear": []}
 
-    for nk in (512, 2048, 4096, 7459):
+    for nk in (() if args.skip_attention else (512, 2048, 4096, 7459)):
         T = nk
         k = torch.randn(B, H, T, D, device=dev, dtype=torch.float16)
         v = torch.randn(B, H, T, D, device=dev, dtype=torch.float16)
