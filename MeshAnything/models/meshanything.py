@@ -74,6 +74,7 @@ class MeshAnything(nn.Module):
         self._dec = DecoderArena(state_dict, device)
         self._tok = TokenizerArena(state_dict, device)
         self._gens = {}
+        self._engines = {}
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def _generator(self, batch: int):
@@ -101,3 +102,44 @@ class MeshAnything(nn.Module):
         self._calls += 1
         self.last_ids = ids
         return self._tok.detokenize(ids, point_feature, self.n_max_triangles)
+
+    # ------------------------------------------------------------------ queue of shapes (continuous batching)
+    @torch.no_grad()
+    def forward_queue(self, pc_normals, sampling: bool = False, slots: int = 8, poll_every: int = 32):
+        """Not in the reference: runs any number of point clouds ([4096,6] each) through
+        `slots` decoder cache slots, refilling a slot as soon as its mesh has hit EOS instead of padding it until the
+        longest mesh of a batch ends (`main.py:137-152` + HF generate).  Returns a list of [n_max_triangles,3,3]
+        tensors in input order; under greedy decoding each equals `forward` on that shape alone."""
+        from meshanything_b200.scheduler import SlotEngine, SlotScheduler
+        if self._dec is None:
+            raise RuntimeError("MeshAnything has no weights: call load_state_dict first")
+        generate_length = self.max_length - self.cond_length
+        key = (int(slots), bool(sampling))
+        feats = {}
+
+        def to_prefix(item):
+            idx, pc = item
+            pc = torch.as_tensor(pc)
+            if not pc.is_cuda:
+                pc = pc.to(self._device, non_blocking=True)
+            point_feature, prefix = self.point_encoder.encode_with_prefix(pc.reshape(1, *pc.shape[-2:]))
+            feats[idx] = point_feature
+            return prefix[0]
+
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._engines[key] = SlotEngine(self._dec, int(slots), self.max_length, generate_length,
+                                                  do_sample=bool(sampling), top_k=50, top_p=0.95, seed=self.seed,
+                                                  eos_id=self.eos_token_id, pad_id=self.pad_token_id)
+        eng.to_prefix = to_prefix
+        eng.samp.seed = self.seed + self._calls
+        eng.reset()
+        self._calls += 1
+        sched = SlotScheduler(eng, int(slots), generate_length, prefix_len=self.cond_length, poll_every=poll_every)
+        out = {}
+        for idx, ids in sched.run(enumerate(pc_normals)):
+            row = torch.full((1, generate_length), self.pad_token_id, dtype=torch.int32, device=self._device)
+            row[0, :ids.numel()] = ids
+            out[idx] = self._tok.detokenize(row, feats.pop(idx), self.n_max_triangles)[0]
+        self.last_queue_stats = sched.stats
+        return [out[i] for i in range(len(out))]

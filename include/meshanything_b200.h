@@ -114,6 +114,28 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
                        const ma_sampling* sampling, int eos_id, int pad_id, void* kv, void* ws, int32_t* out_ids,
                        int32_t* out_lens, const int32_t* forced_ids, void* logits_out, int flags, void* stream);
 
+/* ---- continuous batching over B cache slots (replaces HF generate's "pad finished rows
+ * until the longest sequence ends", transformers generation/utils.py _greedy_search/_sample, for a queue of shapes).
+ * Same kv / ws buffers and sizes as ma_decode_generate; out_ids int32 [B][max_new] is indexed by slot.
+ *   ma_decode_slots_init    every slot free (finished = 1).
+ *   ma_decode_slot_prefill  loads `prefix` (fp32 [257][1024]) into `slot`, clears its out_ids row, picks its first
+ *                           token; the slot is live from the next step on.
+ *   ma_decode_slots_step    n_steps decode steps of all slots; finished slots are frozen (no output, no state change);
+ *                           a slot finishes on eos or after max_new tokens.  max_ctx = the largest number of keys any
+ *                           live slot attends to at the first of these steps (257 + tokens generated so far), an upper
+ *                           bound is fine: it only sizes the attention grid.
+ *   ma_decode_slots_poll    copies finished[B] / lens[B] to host memory and waits for the stream (the one
+ *                           synchronising call; the scheduler calls it every few dozen steps).
+ * Every sequence gets the ids a solo ma_decode_generate would give it (batch-invariant arithmetic). */
+int ma_decode_slots_init(int B, int tmax, int pad_id, void* ws, void* stream);
+int ma_decode_slot_prefill(const ma_decoder_weights* w, const float* prefix, int slot, int B, int tmax, int max_new,
+                           const ma_sampling* sampling, int eos_id, int pad_id, void* kv, void* ws, int32_t* out_ids,
+                           void* stream);
+int ma_decode_slots_step(const ma_decoder_weights* w, int B, int tmax, int max_new, int n_steps, int max_ctx,
+                         const ma_sampling* sampling, int eos_id, int pad_id, void* kv, void* ws, int32_t* out_ids,
+                         int flags, void* stream);
+int ma_decode_slots_poll(int B, int tmax, void* ws, int32_t* finished_host, int32_t* lens_host, void* stream);
+
 /* flags of ma_decode_generate */
 #define MA_GEN_NO_GRAPH 1   /* plain launches instead of a CUDA graph per step */
 #define MA_GEN_NO_FAST 2    /* batch-1: use the general batched kernels instead of the fused GEMV path */

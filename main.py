@@ -74,6 +74,9 @@ def get_args():
                         help="Type of the asset to process (default: pc)")
     for switch in ('--mc', '--sampling'):
         parser.add_argument(switch, default=False, action="store_true")
+    # not in the reference: run this rank's shapes through `batchsize_per_gpu` decoder cache slots, refilling a slot as
+    # soon as its mesh is complete, instead of padded batches (MeshAnything.forward_queue)
+    parser.add_argument('--continuous_batching', default=False, action="store_true")
     return parser.parse_args()
 
 
@@ -153,6 +156,20 @@ if __name__ == "__main__":
     batches = [list(range(i, min(i + bs, len(dataset)))) for i in range(0, len(dataset), bs)]
     begin_time = time.time()
     print("Generation Start!!!")
+
+    def save(item, recon_mesh):
+        recon_mesh = recon_mesh[~torch.isnan(recon_mesh[:, 0, 0])]
+        save_path = os.path.join(checkpoint_dir, f'{item["uid"]}_gen.obj')
+        export_obj(save_path, recon_mesh.cpu().numpy())
+        print(f"{save_path} Over!!")
+
+    if args.continuous_batching:
+        mine = [dataset[i] for i in range(rank, len(dataset), world)]   # shapes are independent: round-robin by rank
+        outs = model.forward_queue((torch.from_numpy(it['pc_normal']) for it in mine), sampling=args.sampling,
+                                   slots=max(1, bs))
+        for it, recon_mesh in zip(mine, outs):
+            save(it, recon_mesh)
+        batches = []
     for bi, idxs in enumerate(batches):
         if bi % world != rank:
             continue
@@ -160,9 +177,5 @@ if __name__ == "__main__":
         pc = torch.from_numpy(np.stack([it['pc_normal'] for it in items]))
         outputs = model(pc, sampling=args.sampling)
         for batch_id, it in enumerate(items):
-            recon_mesh = outputs[batch_id]
-            recon_mesh = recon_mesh[~torch.isnan(recon_mesh[:, 0, 0])]
-            save_path = os.path.join(checkpoint_dir, f'{it["uid"]}_gen.obj')
-            export_obj(save_path, recon_mesh.cpu().numpy())
-            print(f"{save_path} Over!!")
+            save(it, outputs[batch_id])
     print(f"Total time: {time.time() - begin_time}")

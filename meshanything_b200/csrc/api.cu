@@ -45,8 +45,10 @@ struct DecWs {
   int* nkeys;
   SeqState s;
   int* all_done;
-  void* attn_scratch;
+  void* attn_scratch;      // decode steps (M = B rows)
   size_t attn_scratch_bytes;
+  void* attn_scratch_pre;  // prefill passes (M = 257 x sequences): its own area, because the layout (counters, then
+  size_t attn_scratch_pre_bytes;  // partials) depends on M and a slot prefill may follow decode steps
   void* fast;
   void* mega;
   size_t total;
@@ -76,9 +78,10 @@ static DecWs carve(void* base, int B, int tmax, int vocab) {
   w.s.finished = (int*)take((size_t)B * 4);
   w.s.lens = (int*)take((size_t)B * 4);
   w.all_done = (int*)take(256);
-  w.attn_scratch_bytes = std::max(attention_scratch_bytes((int)B, NHEAD, tmax),
-                                  attention_scratch_bytes(PREFIX * std::min(B, PREFILL_SEQS), NHEAD, PREFIX));
+  w.attn_scratch_bytes = attention_scratch_bytes((int)B, NHEAD, tmax);
   w.attn_scratch = take(w.attn_scratch_bytes);
+  w.attn_scratch_pre_bytes = attention_scratch_bytes(PREFIX * std::min(B, PREFILL_SEQS), NHEAD, PREFIX);
+  w.attn_scratch_pre = take(w.attn_scratch_pre_bytes);
   w.fast = take(fast_workspace_bytes());
   w.mega = take(mega_workspace_bytes());
   w.total = off;
@@ -92,6 +95,7 @@ static inline __half* kv_layer(void* kv, int layer, int which, int B, long T) {
 // One pass of the 24 layers over M rows (general batched kernels).
 static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, int B, long T, int M, int rows_per_slot,
                       int slot0, int max_keys, cudaStream_t st) {
+  void* scratch = rows_per_slot > 1 ? ws.attn_scratch_pre : ws.attn_scratch;
   for (int L = 0; L < w->n_layers; L++) {
     __half* kc = kv_layer(kv, L, 0, B, T) + (size_t)slot0 * NHEAD * T * HD;
     __half* vc = kv_layer(kv, L, 1, B, T) + (size_t)slot0 * NHEAD * T * HD;
@@ -99,7 +103,7 @@ static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, in
                       MA_EPI_NONE, st)) return 1;
     if (launch_kv_append(ws.qkv, M, rows_per_slot, ws.nkeys, kc, vc, T, st)) return 1;
     if (launch_attention(ws.qkv, QKV, kc, vc, T, NHEAD, rows_per_slot, nullptr, ws.nkeys, max_keys, M, 0.125f,
-                         ws.attn16, HID, ws.attn_scratch, st)) return 1;
+                         ws.attn16, HID, scratch, st)) return 1;
     if (launch_linear((const __half*)w->wo[L], (const __half*)w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID,
                       MA_EPI_NONE, st)) return 1;
     if (launch_layernorm(ws.hres, ws.y16, w->ln1g[L], w->ln1b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
@@ -116,7 +120,7 @@ static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, in
 struct GraphKey {
   const void *w, *kv, *ws, *out_ids, *forced, *logits_out;
   unsigned long long whash;
-  int B, tmax, max_new, bucket, flags, do_sample, top_k, eos, pad;
+  int B, tmax, max_new, bucket, flags, do_sample, top_k, eos, pad, mode;
   float top_p;
   unsigned long long seed;
   bool operator<(const GraphKey& o) const { return memcmp(this, &o, sizeof(GraphKey)) < 0; }
@@ -151,6 +155,95 @@ static int ensure_globals() {
       return 1;
     }
     g_device = dev;
+  }
+  return 0;
+}
+
+
+// One decode step of the whole batch on the general kernels (embed -> 24 layers -> lm_head -> pick).
+static int enqueue_batched_step(const ma_decoder_weights* w, const DecWs& ws, void* kv, int B, long T, int max_keys,
+                                const SampleArgs& sa, cudaStream_t s) {
+  if (launch_embed_tokens(w, ws.s, B, ws.hres, ws.x16, ws.nkeys, s)) return 1;
+  if (run_layers(w, ws, kv, B, T, B, 1, 0, max_keys, s)) return 1;
+  if (launch_linear((const __half*)w->lm_head, nullptr, ws.x16, HID, ws.logits, w->vocab, B, w->vocab, HID,
+                    MA_EPI_NONE, s)) return 1;
+  return launch_sample(sa, s);
+}
+
+static unsigned long long weights_hash(const ma_decoder_weights* w) {
+  unsigned long long h = 1469598103934665603ull;  // FNV-1a over the pointer table: graphs bake the pointers in
+  const unsigned char* pb = (const unsigned char*)w;
+  for (size_t q = 0; q < sizeof(ma_decoder_weights); q++) h = (h ^ pb[q]) * 1099511628211ull;
+  return h;
+}
+
+// Launch `enqueue` through the per-step graph cache (captured on first use of `key`).
+template <class F>
+static int launch_cached_graph(const GraphKey& key, cudaStream_t st, F&& enqueue) {
+  auto it = g_graphs.find(key);
+  if (it == g_graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(cudaGetLastError()));
+      return 1;
+    }
+    const unsigned long long before = g_launches.load();
+    int erc = enqueue(st);
+    const unsigned long long per_step = g_launches.load() - before;
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (erc || ce != cudaSuccess || !graph) {
+      if (!erc) set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
+      cudaGetLastError();
+      return 1;
+    }
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) {
+      set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
+      return 1;
+    }
+    if (g_graphs.size() > 64) {
+      for (auto& kvp : g_graphs) cudaGraphExecDestroy(kvp.second);
+      g_graphs.clear();
+      g_graph_launches.clear();
+    }
+    it = g_graphs.emplace(key, exec).first;
+    g_launches -= per_step;  // the capture itself launched nothing
+    g_graph_launches[exec] = per_step;
+  }
+  if (cudaGraphLaunch(it->second, st) != cudaSuccess) {
+    set_error("cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  g_launches += g_graph_launches[it->second];
+  return 0;
+}
+
+static void fill_sample_args(SampleArgs& sa, const ma_decoder_weights* w, const DecWs& ws, int B, int max_new,
+                             const ma_sampling* sampling, int eos_id, int pad_id, int32_t* out_ids) {
+  memset(&sa, 0, sizeof(sa));
+  sa.logits = ws.logits; sa.vocab = w->vocab; sa.B = B; sa.max_new = max_new; sa.eos_id = eos_id; sa.pad_id = pad_id;
+  sa.do_sample = sampling ? sampling->do_sample : 0;
+  sa.top_k = sampling ? sampling->top_k : 0;
+  sa.top_p = sampling ? sampling->top_p : 1.0f;
+  sa.seed = sampling ? sampling->seed : 0;
+  sa.s = ws.s; sa.out_ids = out_ids;
+}
+
+static int check_decode_args(const char* who, const ma_decoder_weights* w, int B, int tmax, int max_new) {
+  if (w->n_layers > MA_MAX_LAYERS || w->vocab > 8195 + 61) {
+    set_error("%s: n_layers=%d / vocab=%d unsupported", who, w->n_layers, w->vocab);
+    return 1;
+  }
+  if (B <= 0 || max_new <= 0 || PREFIX + max_new > tmax) {
+    set_error("%s: B=%d, tmax=%d < 257 + max_new=%d", who, B, tmax, max_new);
+    return 1;
+  }
+  if (PREFIX + max_new + 2 > w->npos) {
+    // meshanything.py:97-98: 18259 learned positions (+2 offset rows)
+    set_error("%s: sequence of %d exceeds %d learned positions", who, PREFIX + max_new, w->npos - 2);
+    return 1;
   }
   return 0;
 }
@@ -220,19 +313,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
     set_error("ma_decode_generate: bad arguments");
     return 1;
   }
-  if (w->n_layers > MA_MAX_LAYERS || w->vocab > 8195 + 61) {
-    set_error("ma_decode_generate: n_layers=%d / vocab=%d unsupported", w->n_layers, w->vocab);
-    return 1;
-  }
-  if (PREFIX + max_new > tmax) {
-    set_error("ma_decode_generate: tmax=%d < 257 + max_new=%d", tmax, max_new);
-    return 1;
-  }
-  if (PREFIX + max_new + 2 > w->npos) {
-    // meshanything.py:97-98: 18259 learned positions (+2 offset rows)
-    set_error("ma_decode_generate: sequence of %d exceeds %d learned positions", PREFIX + max_new, w->npos - 2);
-    return 1;
-  }
+  if (check_decode_args("ma_decode_generate", w, B, tmax, max_new)) return 1;
   std::lock_guard<std::mutex> lock(g_mu);
   if (ensure_globals()) return 1;
   cudaStream_t user = (cudaStream_t)stream;
@@ -243,17 +324,13 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   const long T = tmax;
   DecWs ws = carve(ws_, B, tmax, 8195 + 61);
   cudaMemsetAsync(ws.attn_scratch, 0, ws.attn_scratch_bytes, st);
+  cudaMemsetAsync(ws.attn_scratch_pre, 0, ws.attn_scratch_pre_bytes, st);
   cudaMemsetAsync(ws.fast, 0, fast_workspace_bytes(), st);
   if (launch_fill_i32(out_ids, pad_id, (long)B * max_new, st)) return 1;
 
   SampleArgs sa;
-  memset(&sa, 0, sizeof(sa));
-  sa.logits = ws.logits; sa.vocab = w->vocab; sa.B = B; sa.max_new = max_new; sa.eos_id = eos_id; sa.pad_id = pad_id;
-  sa.do_sample = sampling ? sampling->do_sample : 0;
-  sa.top_k = sampling ? sampling->top_k : 0;
-  sa.top_p = sampling ? sampling->top_p : 1.0f;
-  sa.seed = sampling ? sampling->seed : 0;
-  sa.s = ws.s; sa.first = 1; sa.out_ids = out_ids; sa.forced = forced_ids; sa.logits_out = (__half*)logits_out;
+  fill_sample_args(sa, w, ws, B, max_new, sampling, eos_id, pad_id, out_ids);
+  sa.first = 1; sa.forced = forced_ids; sa.logits_out = (__half*)logits_out;
   sa.all_done = ws.all_done;
 
   const bool fast = (B == 1) && !(flags & MA_GEN_NO_FAST);
@@ -282,6 +359,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   const bool use_graph = !(flags & MA_GEN_NO_GRAPH);
   const bool early = !(flags & MA_GEN_NO_EARLY_EXIT) && !forced_ids;
   const int CHECK_EVERY = 64;
+  const unsigned long long whash = use_graph ? weights_hash(w) : 0;  // the struct is read at capture time
   bool flag_pending = false;
   int rc = 0;
   if (mega) {
@@ -298,11 +376,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
     const int max_keys = fast ? tmax : std::min(tmax, bucket * 1024);
     auto enqueue = [&](cudaStream_t s) -> int {
       if (fast) return fast_step_enqueue(w, ws.s, tmax, (__half*)kv, ws.fast, sa, !(flags & MA_GEN_NO_PDL), s);
-      if (launch_embed_tokens(w, ws.s, B, ws.hres, ws.x16, ws.nkeys, s)) return 1;
-      if (run_layers(w, ws, kv, B, T, B, 1, 0, max_keys, s)) return 1;
-      if (launch_linear((const __half*)w->lm_head, nullptr, ws.x16, HID, ws.logits, w->vocab, B, w->vocab, HID,
-                        MA_EPI_NONE, s)) return 1;
-      return launch_sample(sa, s);
+      return enqueue_batched_step(w, ws, kv, B, T, max_keys, sa, s);
     };
     if (!use_graph) {
       rc = enqueue(st);
@@ -313,48 +387,8 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
       key.B = B; key.tmax = tmax; key.max_new = max_new; key.bucket = bucket; key.flags = flags;
       key.do_sample = sa.do_sample; key.top_k = sa.top_k; key.eos = eos_id; key.pad = pad_id; key.top_p = sa.top_p;
       key.seed = sa.seed;
-      {  // the weights struct is read at capture time: key on its contents, not only its address
-        unsigned long long h = 1469598103934665603ull;
-        const unsigned char* pb = (const unsigned char*)w;
-        for (size_t q = 0; q < sizeof(ma_decoder_weights); q++) h = (h ^ pb[q]) * 1099511628211ull;
-        key.whash = h;
-      }
-      auto it = g_graphs.find(key);
-      if (it == g_graphs.end()) {
-        cudaGraph_t graph = nullptr;
-        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-          set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(cudaGetLastError()));
-          return 1;
-        }
-        const unsigned long long before = g_launches.load();
-        int erc = enqueue(st);
-        const unsigned long long per_step = g_launches.load() - before;
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (erc || ce != cudaSuccess || !graph) {
-          if (!erc) set_error("cudaStreamEndCapture: %s", cudaGetErrorString(ce));
-          cudaGetLastError();
-          return 1;
-        }
-        cudaGraphExec_t exec = nullptr;
-        ce = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) {
-          set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ce));
-          return 1;
-        }
-        if (g_graphs.size() > 64) {
-          for (auto& kvp : g_graphs) cudaGraphExecDestroy(kvp.second);
-          g_graphs.clear();
-        }
-        it = g_graphs.emplace(key, exec).first;
-        g_launches -= per_step;  // the capture itself launched nothing
-        g_graph_launches[exec] = per_step;
-      }
-      if (cudaGraphLaunch(it->second, st) != cudaSuccess) {
-        set_error("cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
-        return 1;
-      }
-      g_launches += g_graph_launches[it->second];
+      key.whash = whash;
+      if (launch_cached_graph(key, st, enqueue)) return 1;
     }
     if (early && (i % CHECK_EVERY) == 0) {
       // lagged, non-blocking early-exit poll: look at the flag copied CHECK_EVERY steps ago
@@ -374,6 +408,126 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   cudaEventRecord(g_ev_out, st);
   cudaStreamWaitEvent(user, g_ev_out, 0);
   return check_launch("ma_decode_generate") ? 0 : 1;
+}
+
+
+// ---- continuous batching: B cache slots, each running its own sequence ------------------
+// The host scheduler (meshanything_b200/scheduler.py) refills a slot as soon as its sequence has finished instead of
+// padding it until the longest sequence of the batch ends (HF generate semantics, a10).  Rows never interact and the
+// kernels are batch-invariant, so every sequence gets bit-identical ids to a solo ma_decode_generate.
+
+static int slots_enter(void* stream, cudaStream_t* st) {
+  if (ensure_globals()) return 1;
+  cudaEventRecord(g_ev_in, (cudaStream_t)stream);
+  cudaStreamWaitEvent(g_stream, g_ev_in, 0);
+  *st = g_stream;
+  return 0;
+}
+static int slots_leave(void* stream, const char* who) {
+  cudaEventRecord(g_ev_out, g_stream);
+  cudaStreamWaitEvent((cudaStream_t)stream, g_ev_out, 0);
+  return check_launch(who) ? 0 : 1;
+}
+
+int ma_decode_slots_init(int B, int tmax, int pad_id, void* ws_, void* stream) {
+  if (!ws_ || B <= 0 || tmax < PREFIX + 1) {
+    set_error("ma_decode_slots_init: bad arguments");
+    return 1;
+  }
+  std::lock_guard<std::mutex> lock(g_mu);
+  cudaStream_t st;
+  if (slots_enter(stream, &st)) return 1;
+  DecWs ws = carve(ws_, B, tmax, 8195 + 61);
+  cudaMemsetAsync(ws.attn_scratch, 0, ws.attn_scratch_bytes, st);
+  cudaMemsetAsync(ws.attn_scratch_pre, 0, ws.attn_scratch_pre_bytes, st);
+  // every slot starts free: finished, nothing generated, a valid (pad) token at a valid position
+  if (launch_fill_i32(ws.s.pos, PREFIX, B, st) || launch_fill_i32(ws.s.gen, 0, B, st) ||
+      launch_fill_i32(ws.s.tok, pad_id, B, st) || launch_fill_i32(ws.s.finished, 1, B, st) ||
+      launch_fill_i32(ws.s.lens, 0, B, st)) return 1;
+  return slots_leave(stream, "ma_decode_slots_init");
+}
+
+int ma_decode_slot_prefill(const ma_decoder_weights* w, const float* prefix, int slot, int B, int tmax, int max_new,
+                           const ma_sampling* sampling, int eos_id, int pad_id, void* kv, void* ws_, int32_t* out_ids,
+                           void* stream) {
+  if (!w || !prefix || !kv || !ws_ || !out_ids || slot < 0 || slot >= B) {
+    set_error("ma_decode_slot_prefill: bad arguments (slot %d of %d)", slot, B);
+    return 1;
+  }
+  if (check_decode_args("ma_decode_slot_prefill", w, B, tmax, max_new)) return 1;
+  std::lock_guard<std::mutex> lock(g_mu);
+  cudaStream_t st;
+  if (slots_enter(stream, &st)) return 1;
+  const long T = tmax;
+  DecWs ws = carve(ws_, B, tmax, 8195 + 61);
+  if (launch_fill_i32(out_ids + (size_t)slot * max_new, pad_id, max_new, st)) return 1;
+  if (launch_embed_prefix(w, prefix, 1, ws.hres, ws.x16, ws.nkeys, st)) return 1;
+  if (run_layers(w, ws, kv, B, T, PREFIX, PREFIX, slot, PREFIX, st)) return 1;
+  __half* last = ws.lastx16 + (size_t)slot * HID;
+  if (launch_gather_rows(ws.x16, HID, PREFIX - 1, PREFIX, 1, last, st)) return 1;
+  if (launch_linear((const __half*)w->lm_head, nullptr, last, HID, ws.logits + (size_t)slot * w->vocab, w->vocab, 1,
+                    w->vocab, HID, MA_EPI_NONE, st)) return 1;
+  SampleArgs sa;
+  fill_sample_args(sa, w, ws, B, max_new, sampling, eos_id, pad_id, out_ids);
+  sa.first = 1; sa.row0 = slot; sa.nrows = 1; sa.slots = 1;
+  if (launch_sample(sa, st)) return 1;
+  return slots_leave(stream, "ma_decode_slot_prefill");
+}
+
+int ma_decode_slots_step(const ma_decoder_weights* w, int B, int tmax, int max_new, int n_steps, int max_ctx,
+                         const ma_sampling* sampling, int eos_id, int pad_id, void* kv, void* ws_, int32_t* out_ids,
+                         int flags, void* stream) {
+  if (!w || !kv || !ws_ || !out_ids || n_steps < 0 || max_ctx < PREFIX + 1) {
+    set_error("ma_decode_slots_step: bad arguments");
+    return 1;
+  }
+  if (check_decode_args("ma_decode_slots_step", w, B, tmax, max_new)) return 1;
+  std::lock_guard<std::mutex> lock(g_mu);
+  cudaStream_t st;
+  if (slots_enter(stream, &st)) return 1;
+  const long T = tmax;
+  DecWs ws = carve(ws_, B, tmax, 8195 + 61);
+  SampleArgs sa;
+  fill_sample_args(sa, w, ws, B, max_new, sampling, eos_id, pad_id, out_ids);
+  sa.slots = 1;
+  const bool use_graph = !(flags & MA_GEN_NO_GRAPH);
+  const unsigned long long whash = use_graph ? weights_hash(w) : 0;
+  for (int i = 0; i < n_steps; i++) {
+    const int ctx = std::min(tmax, max_ctx + i);   // upper bound of the keys any live slot sees at this step
+    const int bucket = (ctx + 1023) / 1024;
+    const int max_keys = std::min(tmax, bucket * 1024);
+    auto enqueue = [&](cudaStream_t s) -> int { return enqueue_batched_step(w, ws, kv, B, T, max_keys, sa, s); };
+    if (!use_graph) {
+      if (enqueue(st)) return 1;
+    } else {
+      GraphKey key;
+      memset(&key, 0, sizeof(key));
+      key.w = w; key.kv = kv; key.ws = ws_; key.out_ids = out_ids;
+      key.B = B; key.tmax = tmax; key.max_new = max_new; key.bucket = bucket; key.flags = flags; key.mode = 1;
+      key.do_sample = sa.do_sample; key.top_k = sa.top_k; key.eos = eos_id; key.pad = pad_id; key.top_p = sa.top_p;
+      key.seed = sa.seed; key.whash = whash;
+      if (launch_cached_graph(key, st, enqueue)) return 1;
+    }
+  }
+  return slots_leave(stream, "ma_decode_slots_step");
+}
+
+int ma_decode_slots_poll(int B, int tmax, void* ws_, int32_t* finished_host, int32_t* lens_host, void* stream) {
+  if (!ws_ || !finished_host || !lens_host || B <= 0) {
+    set_error("ma_decode_slots_poll: bad arguments");
+    return 1;
+  }
+  std::lock_guard<std::mutex> lock(g_mu);
+  cudaStream_t st;
+  if (slots_enter(stream, &st)) return 1;
+  DecWs ws = carve(ws_, B, tmax, 8195 + 61);
+  cudaMemcpyAsync(finished_host, ws.s.finished, sizeof(int) * B, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(lens_host, ws.s.lens, sizeof(int) * B, cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) {
+    set_error("ma_decode_slots_poll: %s", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
+  return slots_leave(stream, "ma_decode_slots_poll");
 }
 
 

@@ -221,7 +221,9 @@ int launch_attention_ex(const __half* q, int ldq, const __half* K, const __half*
   a.q = q; a.ldq = ldq; a.K = K; a.V = V; a.T = T; a.H = H;
   a.rows_per_slot = rows_per_slot > 0 ? rows_per_slot : 1;
   a.slots = slots; a.nkeys = nkeys; a.scale = scale; a.out = out; a.ldo = ldo;
-  // scratch layout: counters first (must be zero on first use), then the chunk partials
+  // scratch layout: counters first (must be zero on first use; every launch leaves them zero again), then the chunk
+  // partials.  The split depends on M: a scratch area that serves launches with DIFFERENT M must be zeroed between
+  // them (partials of one layout land on the counters of the other) -- api.cu keeps one area per M instead.
   a.counters = reinterpret_cast<int*>(scratch);
   size_t coff = ((size_t)M * H * sizeof(int) + 255) & ~(size_t)255;
   a.part = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + coff);

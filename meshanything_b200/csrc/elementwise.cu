@@ -223,9 +223,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
   __shared__ int keepi[KEEP_MAX], sorti[KEEP_MAX];
   __shared__ int s_bin, s_above;
   extern __shared__ unsigned short keys[];  // [vocab] order-preserving keys of the row (sampling only)
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x + a.row0, tid = threadIdx.x;
   const __half* lg = a.logits + (long)b * a.vocab;
   const int gen = a.first ? 0 : a.s.gen[b];
+  if (a.slots && !a.first && a.s.finished[b]) return;  // frozen slot (uniform per CTA): nothing to pick or advance
 
   if (a.logits_out) {
     __half* dst = a.logits_out + ((long)gen * a.B + b) * a.vocab;
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
     if (a.out_ids && gen < a.max_new) a.out_ids[(long)b * a.max_new + gen] = tok;
     if (a.s.lens) {
       if (!fin) a.s.lens[b] = gen + 1;
-      if (!fin && tok == a.eos_id) fin = 1;
+      if (!fin && (tok == a.eos_id || (a.slots && gen + 1 >= a.max_new))) fin = 1;
       a.s.finished[b] = fin;
       a.s.tok[b] = tok;
       a.s.gen[b] = gen + 1;
@@ -399,7 +400,7 @@ int launch_sample(const SampleArgs& a, cudaStream_t st) {
     set_error("sampling supports vocab <= 16384 (got %d)", a.vocab);
     return 1;
   }
-  sample_kernel<<<a.B, SAMPLE_THREADS, dyn, st>>>(a);
+  sample_kernel<<<a.nrows > 0 ? a.nrows : a.B, SAMPLE_THREADS, dyn, st>>>(a);
   count_launch();
   return check_launch("sample_kernel") ? 0 : 1;
 }

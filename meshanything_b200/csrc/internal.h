@@ -68,6 +68,9 @@ struct SampleArgs {
   int* nkeys_next;       // optional [B]: keys visible to the next step (pos + 1), for the batch-1 fast path
   int32_t* support_out;  // test hook [B][256]: token ids that survive top-k/top-p (descending), -1 padded
   int32_t* token_out;    // test hook [B]: the picked token
+  int row0, nrows;       // rows [row0, row0 + nrows) are processed (nrows = 0: all B rows)
+  int slots;             // 1: continuous batching -- finished rows are frozen (no state advance, no output write)
+                         //    and a row also finishes when it reaches max_new tokens
 };
 int launch_sample(const SampleArgs& a, cudaStream_t st);
 int launch_fill_i32(int32_t* p, int v, long n, cudaStream_t st);

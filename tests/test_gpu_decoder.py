@@ -237,3 +237,36 @@ def test_long_context_config5_golden():
     gen2 = Generator(arena, 2, 257 + n)
     ids2, _ = gen2.generate(two, n)
     assert ids2[0].cpu().tolist() == gold
+
+
+@gpu
+@pytest.mark.parametrize("slots,poll_every,flags", [(2, 4, 0), (3, 7, 1), (1, 5, 0)])
+def test_continuous_batching_equals_solo_generation(small, slots, poll_every, flags):
+    """a queue of 6 prefixes through `slots` cache slots with refill on EOS.  EOS is re-declared as a
+    token each sequence emits at a different step, so lengths differ; every sequence must come back with exactly the
+    ids (and length) a solo `Generator.generate` gives it."""
+    from meshanything_b200.decoder import Generator
+    from meshanything_b200.scheduler import SlotEngine, SlotScheduler
+    _, arena, _ = small
+    n, NP = 40, 6
+    prefixes = random_prefix(NP, seed=23).to(_dev())
+    solo_gen = Generator(arena, 1, 257 + n)
+    free = [solo_gen.generate(prefixes[i:i + 1], n)[0][0].cpu().tolist() for i in range(NP)]
+    # an eos that shows up at different steps in different sequences (and not at all in some)
+    cand = {}
+    for t in set(free[0][3:]) | set(free[1][10:]) | set(free[2][20:]):
+        firsts = [seq.index(t) if t in seq else None for seq in free]
+        cand[t] = firsts
+    eos = max(cand, key=lambda t: len({f for f in cand[t] if f is not None}))
+    solo = []
+    for i in range(NP):
+        ids, lens = solo_gen.generate(prefixes[i:i + 1], n, eos_id=eos)
+        solo.append(ids[0, :int(lens[0])].cpu().tolist())
+    assert len({len(s) for s in solo}) >= 2, "test needs sequences of different lengths"
+    eng = SlotEngine(arena, slots, 257 + n, n, eos_id=eos, flags=flags)
+    sched = SlotScheduler(eng, slots, n, poll_every=poll_every)
+    got = {idx: ids.cpu().tolist() for idx, ids in sched.run([prefixes[i] for i in range(NP)])}
+    assert sorted(got) == list(range(NP))
+    for i in range(NP):
+        assert got[i] == solo[i], (i, len(got[i]), len(solo[i]))
+    assert sched.stats.prefills == NP
