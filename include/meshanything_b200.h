@@ -154,9 +154,20 @@ int ma_decoder_debug(void* ws, int B, int tmax, int what, void* host_out, int nb
  * not bit for bit).  M >= 64, N % 128 == 0, K % 64 == 0.  Used by ma_encoder_forward / ma_detokenize. */
 int ma_linear_tc_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
                      int epilogue, void* stream);
-/* 1 (default): encoder / detokenizer GEMMs run on the tensor cores; 0: canonical CUDA-core kernel.  Returns the
- * previous setting. */
+/* 0: canonical CUDA-core kernels everywhere; 1: encoder / detokenizer GEMMs on the tensor cores; 2: their attention
+ * too (ma_attention_tc_f16).  Returns the previous setting. */
 int ma_set_tensor_cores(int enable);
+
+/* Dense non-causal attention on the tensor cores (tcgen05 flash attention; replaces F.scaled_dot_product_attention of
+ * transformer_blocks.py:57-74,166-185 and BERT's attention in meshanything.py:62-64).  q fp16 [n_slots*rows_per_slot][ldq]
+ * (head h at columns 64h..64h+63), K fp16 [n_slots][H][T][64], Vt fp16 [n_slots][H][64][Tpad] = V transposed, zero for
+ * keys >= nkeys, Tpad a multiple of 64 and >= nkeys rounded up to 128; every query of a slot sees the first nkeys
+ * keys of that slot.  out fp16 [rows][ldo].  Hardware accumulation order: compared under a tolerance. */
+int ma_attention_tc_f16(const void* q, int ldq, const void* K, const void* Vt, long T, long Tpad, int H,
+                        int rows_per_slot, int n_slots, int nkeys, float scale, void* out, int ldo, void* stream);
+/* Vt[((slot*H + h)*64 + d)*Tpad + t] = src[(slot*n + t)*ld + col0 + h*head_stride + d] for t < n, 0 for n <= t < Tpad */
+int ma_transpose_heads_f16(const void* src, int ld, int col0, int head_stride, int H, int n, long Tpad, int n_slots,
+                           void* dst, void* stream);
 
 /* ---- Michelangelo point-cloud encoder (a1-a8) ----------------------------------------------- */
 

@@ -40,6 +40,7 @@ EXPORTS = [
     "ma_attention_scratch_bytes", "ma_attention_f16", "ma_kv_cache_bytes", "ma_decoder_workspace_bytes",
     "ma_decode_generate", "ma_decoder_debug", "ma_encoder_workspace_bytes", "ma_encoder_forward",
     "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores", "ma_sample_tokens",
+    "ma_attention_tc_f16", "ma_transpose_heads_f16",
     "ma_decode_slots_init", "ma_decode_slot_prefill", "ma_decode_slots_step", "ma_decode_slots_poll",
 ]
 
@@ -73,6 +74,9 @@ def lib():
     L.ma_decode_generate.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.POINTER(Sampling),
                                      C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]
     L.ma_sample_tokens.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(Sampling), _vp, _vp, _vp]
+    L.ma_attention_tc_f16.argtypes = [_vp, C.c_int, _vp, _vp, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_float, _vp, C.c_int, _vp]
+    L.ma_transpose_heads_f16.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _vp, _vp]
     L.ma_decode_slots_init.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.ma_decode_slot_prefill.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(Sampling), C.c_int, C.c_int, _vp, _vp, _vp, _vp]
@@ -138,6 +142,30 @@ def linear_tc_f16(w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor
     out = torch.empty((M, N), dtype=torch.float16, device=x.device)
     check(lib().ma_linear_tc_f16(ptr(w), ptr(bias), ptr(x), x.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
                                  stream_ptr()), "ma_linear_tc_f16")
+    return out
+
+
+def transpose_heads_f16(src: torch.Tensor, col0: int, head_stride: int, H: int, n: int, n_slots: int) -> torch.Tensor:
+    """src fp16 [n_slots*n, ld] -> V^T fp16 [n_slots, H, 64, Tpad] (Tpad = n rounded up to 128, zero padded)."""
+    _need_cuda(src)
+    Tpad = (n + 127) // 128 * 128
+    dst = torch.empty((n_slots, H, 64, Tpad), dtype=torch.float16, device=src.device)
+    check(lib().ma_transpose_heads_f16(ptr(src), src.stride(0), col0, head_stride, H, n, Tpad, n_slots, ptr(dst),
+                                       stream_ptr()), "ma_transpose_heads_f16")
+    return dst
+
+
+def attention_tc_f16(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, nkeys: int, rows_per_slot: int,
+                     scale: float = 0.125) -> torch.Tensor:
+    """q [n_slots*rows_per_slot, H*64]; k [n_slots, H, T, 64]; vt [n_slots, H, 64, Tpad] (V transposed, zero beyond
+    nkeys) -> [rows, H*64], on the tcgen05 tensor cores."""
+    _need_cuda(q, k, vt)
+    S, H, T, _ = k.shape
+    Tpad = vt.shape[3]
+    assert q.is_contiguous() and k.is_contiguous() and vt.is_contiguous() and q.shape[0] == S * rows_per_slot
+    out = torch.empty_like(q)
+    check(lib().ma_attention_tc_f16(ptr(q), q.stride(0), ptr(k), ptr(vt), T, Tpad, H, rows_per_slot, S, nkeys,
+                                    C.c_float(scale), ptr(out), out.stride(0), stream_ptr()), "ma_attention_tc_f16")
     return out
 
 

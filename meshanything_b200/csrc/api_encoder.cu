@@ -69,13 +69,32 @@ static EncWs carve_enc(void* base, int Bc) {
 
 #define TRY(x) do { if (x) return 1; } while (0)
 
-static int g_use_tc = 1;  // dense contractions of the encoder / detokenizer on tcgen05 (ma_set_tensor_cores)
+static int g_use_tc = 2;  // 0: canonical CUDA-core kernels; 1: GEMMs of the encoder / detokenizer on tcgen05;
+                          // 2: their attention on tcgen05 too (ma_set_tensor_cores)
 
 // nn.Linear of the tolerance-checked stages: tensor cores when the shape allows, canonical CUDA-core kernel otherwise
 static int enc_linear(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
                       int K, int epi, cudaStream_t st) {
   if (g_use_tc && linear_tc_supported(M, N, K, ldx, ldy, x, W, y)) return launch_linear_tc(W, bias, x, ldx, y, ldy, M, N, K, epi, st);
   return launch_linear(W, bias, x, ldx, y, ldy, M, N, K, epi, st);
+}
+
+// Dense attention of n_slots x rows_per_slot queries over the n keys of their slot.  q [rows][ldq] (head h at 64h), kh
+// [slot][H][n][64] already scattered; V is still in its source matrix (vsrc, vld, vcol0, vstride as for
+// scatter_heads) and is laid out here the way the chosen kernel wants it: transposed + zero-padded for tcgen05, head-
+// major for the canonical kernel.
+static int enc_attention(const __half* q, int ldq, const __half* kh, const __half* vsrc, int vld, int vcol0,
+                         int vstride, __half* vbuf, int n, int rows_per_slot, int n_slots, const int* nkeys,
+                         __half* out, void* scratch, cudaStream_t st) {
+  const long Tpad = ((long)n + 127) / 128 * 128;
+  if (g_use_tc >= 2 && attention_tc_supported(ldq, EW, n, Tpad, n, q, kh, vbuf, out)) {
+    TRY(launch_scatter_heads_t(vsrc, vld, vcol0, vstride, EH, n, Tpad, n_slots, vbuf, st));
+    return launch_attention_tc(q, ldq, kh, vbuf, n, Tpad, EH, rows_per_slot, n_slots, n, 0.125f, out, EW, st);
+  }
+  const long rows = (long)n_slots * n;
+  TRY(launch_scatter_heads(vsrc, vld, vcol0, vstride, EH, n, n, vbuf, rows, st));
+  return launch_attention(q, ldq, kh, vbuf, n, EH, rows_per_slot, nullptr, nkeys, n, n_slots * rows_per_slot, 0.125f, out,
+                          EW, scratch, st);
 }
 
 // x += c_proj(attn(c_qkv(ln_1 x))) ; x += c_proj(gelu(c_fc(ln_2 x)))   (transformer_blocks.py:109-112)
@@ -88,9 +107,8 @@ static int miche_block(const ma_miche_block& b, const EncWs& w, int Bc, int n, b
   // qkv viewed [B,n,12,192]: head h = columns 192h .. 192h+191 = q | k | v  (transformer_blocks.py:60-62)
   TRY(launch_scatter_heads(w.qkv16, 3 * EW, 0, 192, EH, 1, 1, w.qh, M, st));
   TRY(launch_scatter_heads(w.qkv16, 3 * EW, 64, 192, EH, n, n, w.kh, M, st));
-  TRY(launch_scatter_heads(w.qkv16, 3 * EW, 128, 192, EH, n, n, w.vh, M, st));
   TRY(launch_fill_i32(w.nkeys, n, M, st));
-  TRY(launch_attention(w.qh, EW, w.kh, w.vh, n, EH, n, nullptr, w.nkeys, n, M, 0.125f, w.attn16, EW, w.attn_scratch, st));
+  TRY(enc_attention(w.qh, EW, w.kh, w.qkv16, 3 * EW, 128, 192, w.vh, n, n, Bc, w.nkeys, w.attn16, w.attn_scratch, st));
   TRY(enc_linear((const __half*)b.c_proj_w, (const __half*)b.c_proj_b, w.attn16, EW, w.y16, EW, M, EW, EW,
                     MA_EPI_NONE, st));
   TRY(launch_residual_add(fp16_stream ? nullptr : w.x32, w.x16r, w.y16, (long)M * EW, st));
@@ -120,10 +138,9 @@ static int encoder_chunk(const ma_encoder_weights* e, const __half* pc, int Bc, 
   TRY(enc_linear((const __half*)e->ckv_w, nullptr, w.lnd16, EW, w.kv16, 2 * EW, (int)P, 2 * EW, EW, MA_EPI_NONE, st));
   // kv viewed [B,4096,12,128]: head h = columns 128h..: k | v  (transformer_blocks.py:171-173)
   TRY(launch_scatter_heads(w.kv16, 2 * EW, 0, 128, EH, NPTS, NPTS, w.kh, P, st));
-  TRY(launch_scatter_heads(w.kv16, 2 * EW, 64, 128, EH, NPTS, NPTS, w.vh, P, st));
   TRY(launch_fill_i32(w.nkeys, NPTS, R, st));
-  TRY(launch_attention(w.q16, EW, w.kh, w.vh, NPTS, EH, NLAT, nullptr, w.nkeys, NPTS, R, 0.125f, w.attn16, EW,
-                       w.attn_scratch, st));
+  TRY(enc_attention(w.q16, EW, w.kh, w.kv16, 2 * EW, 64, 128, w.vh, NPTS, NLAT, Bc, w.nkeys, w.attn16, w.attn_scratch,
+                    st));
   TRY(enc_linear((const __half*)e->cproj_w, (const __half*)e->cproj_b, w.attn16, EW, w.y16, EW, R, EW, EW,
                     MA_EPI_NONE, st));
   TRY(launch_residual_add(w.x32, nullptr, w.y16, (long)R * EW, st));
@@ -185,7 +202,7 @@ static DetWs carve_det(void* base, int Bc, int F) {
   w.qkv16 = c.take<__half>(R * 3 * EW);
   w.qh = c.take<__half>(R * EW);
   w.kh = c.take<__half>(R * EW);
-  w.vh = c.take<__half>(R * EW);
+  w.vh = c.take<__half>((size_t)Bc * ((S + 127) / 128 * 128) * EW);  // room for V^T padded to 128 keys (tcgen05 path)
   w.attn16 = c.take<__half>(R * EW);
   w.y16 = c.take<__half>(R * EW);
   w.f16 = c.take<__half>(R * 4 * EW);
@@ -231,9 +248,8 @@ static int detok_chunk(const ma_tokenizer_weights* t, const int32_t* gen_ids, in
                       st));
     TRY(launch_scatter_heads(w.qkv16, 3 * EW, 0, 64, EH, 1, 1, w.qh, R, st));
     TRY(launch_scatter_heads(w.qkv16, 3 * EW, EW, 64, EH, S, S, w.kh, R, st));
-    TRY(launch_scatter_heads(w.qkv16, 3 * EW, 2 * EW, 64, EH, S, S, w.vh, R, st));
-    TRY(launch_attention(w.qh, EW, w.kh, w.vh, S, EH, S, nullptr, w.nkeys, S, R, 0.125f, w.attn16, EW, w.attn_scratch,
-                         st));
+    TRY(enc_attention(w.qh, EW, w.kh, w.qkv16, 3 * EW, 2 * EW, 64, w.vh, S, S, Bc, w.nkeys, w.attn16, w.attn_scratch,
+                      st));
     TRY(enc_linear((const __half*)l.out_w, (const __half*)l.out_b, w.attn16, EW, w.y16, EW, R, EW, EW, MA_EPI_NONE, st));
     TRY(launch_layernorm(w.x32, w.y16, l.n1_g, l.n1_b, 1e-12f, R, EW, w.x32, w.x16, st));
     TRY(enc_linear((const __half*)l.l1_w, (const __half*)l.l1_b, w.x16, EW, w.f16, 4 * EW, R, 4 * EW, EW, MA_EPI_GELU,
@@ -258,8 +274,20 @@ extern "C" {
 
 int ma_set_tensor_cores(int enable) {
   const int old = g_use_tc;
-  g_use_tc = enable ? 1 : 0;
+  g_use_tc = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   return old;
+}
+
+int ma_attention_tc_f16(const void* q, int ldq, const void* K, const void* Vt, long T, long Tpad, int H,
+                        int rows_per_slot, int n_slots, int nkeys, float scale, void* out, int ldo, void* stream) {
+  return launch_attention_tc((const __half*)q, ldq, (const __half*)K, (const __half*)Vt, T, Tpad, H, rows_per_slot,
+                             n_slots, nkeys, scale, (__half*)out, ldo, (cudaStream_t)stream);
+}
+
+int ma_transpose_heads_f16(const void* src, int ld, int col0, int head_stride, int H, int n, long Tpad, int n_slots,
+                           void* dst, void* stream) {
+  return launch_scatter_heads_t((const __half*)src, ld, col0, head_stride, H, n, Tpad, n_slots, (__half*)dst,
+                                (cudaStream_t)stream);
 }
 
 int ma_linear_tc_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,

@@ -12,10 +12,8 @@
 //                            tcgen05.commit -> frees the stage / signals the epilogue
 //   warps 2-5 epilogue      (TMEM lane quadrant = warp % 4): tcgen05.ld 32x32b.x32 -> + bias -> ReLU/GELU -> fp16 -> global
 // Both operands are K-major ([rows][K] row-major), so D = A * B^T needs no transpose.  TMA zero-fills rows beyond M.
-#include <cuda.h>
-
-#include "canon.cuh"
 #include "internal.h"
+#include "tc_common.cuh"
 
 namespace ma {
 
@@ -28,58 +26,6 @@ struct alignas(1024) TcSmem {
   uint64_t full[TC_STAGES], empty[TC_STAGES], tmem_full;
   uint32_t tmem_base;
 };
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// shared-memory matrix descriptor: K-major tile, rows of 128 bytes, SWIZZLE_128B, 8-row groups 1024 bytes apart
-__device__ __forceinline__ uint64_t umma_desc(const void* smem_ptr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_u32(smem_ptr) & 0x3FFFF) >> 4);  // start address
-  d |= (uint64_t)1 << 16;                                // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset
-  d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 __device__ __forceinline__ float gelu_erf_tc(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -188,10 +134,24 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
-static int make_map(CUtensorMap* map, const void* base, int rows, int K, long ld) {
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+static int tc_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled not available");
+    cudaGetLastError();
+    return 1;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+
+int tc_make_map(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows, int box_cols) {
+  if (tc_init()) return 1;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -210,19 +170,13 @@ bool linear_tc_supported(int M, int N, int K, int ldx, int ldy, const void* x, c
 
 int launch_linear_tc(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
                      int K, int epi, cudaStream_t st) {
-  if (!g_encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-      set_error("cuTensorMapEncodeTiled not available");
-      cudaGetLastError();
-      return 1;
-    }
-    g_encode = (EncodeTiledFn)fn;
+  static bool attr_done = false;
+  if (!attr_done) {
     cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem) + 1024);
+    attr_done = true;
   }
   CUtensorMap ma, mb;
-  if (make_map(&ma, x, M, K, ldx) || make_map(&mb, W, N, K, K)) return 1;
+  if (tc_make_map(&ma, x, M, K, ldx, TC_BM, TC_BK) || tc_make_map(&mb, W, N, K, K, TC_BN, TC_BK)) return 1;
   dim3 grid(N / TC_BN, (M + TC_BM - 1) / TC_BM);
   gemm_tc_kernel<<<grid, TC_THREADS, sizeof(TcSmem) + 1024, st>>>(ma, mb, bias, y, ldy, M, N, K, epi);
   count_launch();

