@@ -169,7 +169,7 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     from meshanything_b200 import capi
-    from meshanything_b200.decoder import DecoderArena, Generator
+    from meshanything_b200.decoder import Generator
 
     import argparse as _ap
     from meshanything_b200.checkpoint import all_specs

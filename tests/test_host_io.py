@@ -1,6 +1,5 @@
 """not gpu: host-side pre/post-processing that main.py shares with the reference (main.py:15-58,156-175; mesh_to_pc.py)."""
 import os
-import sys
 
 import numpy as np
 import pytest

@@ -2,7 +2,6 @@
 import os
 
 import numpy as np
-import pytest
 import torch
 
 from tests.util import decoder_sd, random_prefix
