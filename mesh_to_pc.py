@@ -2,7 +2,8 @@
 
 Uses trimesh / mesh2sdf / skimage when they are installed (same calls as the reference); otherwise a
 small numpy implementation of area-weighted surface sampling (what `trimesh.Trimesh.sample` does) is
-used and `marching_cubes=True` raises (mesh2sdf is required for the watertight conversion).
+used (OBJ and ASCII/binary PLY readers included) and `marching_cubes=True` raises (mesh2sdf is required for the
+watertight conversion).
 """
 import numpy as np
 
@@ -56,12 +57,85 @@ class SimpleMesh:
         return SimpleMesh(vs, fs)
 
 
+    _PLY_TYPES = {"char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2",
+                  "ushort": "u2", "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4",
+                  "float": "f4", "float32": "f4", "double": "f8", "float64": "f8"}
+
+    @staticmethod
+    def load_ply(path):
+        """ASCII and binary (little/big endian) PLY: `vertex` (x, y, z among any other scalar properties) and `face`
+        (one list property of vertex indices, polygons fan-triangulated).  Other elements are skipped."""
+        T = SimpleMesh._PLY_TYPES
+        with open(path, "rb") as f:
+            if f.readline().strip() != b"ply":
+                raise ValueError(f"{path}: not a PLY file")
+            fmt, elements = None, []
+            while True:
+                line = f.readline()
+                if not line:
+                    raise ValueError(f"{path}: truncated PLY header")
+                p = line.decode("ascii", "replace").split()
+                if not p or p[0] in ("comment", "obj_info"):
+                    continue
+                if p[0] == "format":
+                    fmt = p[1]
+                elif p[0] == "element":
+                    elements.append({"name": p[1], "count": int(p[2]), "props": []})
+                elif p[0] == "property":
+                    if p[1] == "list":
+                        elements[-1]["props"].append(("list", p[4], T[p[2]], T[p[3]]))
+                    else:
+                        elements[-1]["props"].append(("scalar", p[2], T[p[1]]))
+                elif p[0] == "end_header":
+                    break
+            if fmt not in ("ascii", "binary_little_endian", "binary_big_endian"):
+                raise ValueError(f"{path}: unsupported PLY format {fmt!r}")
+            end = ">" if fmt == "binary_big_endian" else "<"
+            verts, faces = None, []
+            for el in elements:
+                n, props = el["count"], el["props"]
+                has_list = any(pr[0] == "list" for pr in props)
+                if fmt == "ascii":
+                    rows = [f.readline().split() for _ in range(n)]
+                    if el["name"] == "vertex":
+                        names = [pr[1] for pr in props]
+                        ix = [names.index(c) for c in "xyz"]
+                        verts = np.array([[float(r[i]) for i in ix] for r in rows], dtype=np.float64).reshape(-1, 3)
+                    elif el["name"] == "face":
+                        for r in rows:   # list property first (the usual layout); scalar face properties follow it
+                            k = int(r[0])
+                            ids = [int(x) for x in r[1:1 + k]]
+                            faces.extend([ids[0], ids[j], ids[j + 1]] for j in range(1, k - 1))
+                    continue
+                if not has_list:
+                    dt = np.dtype([(pr[1], end + pr[2]) for pr in props])
+                    block = np.frombuffer(f.read(dt.itemsize * n), dtype=dt, count=n)
+                    if el["name"] == "vertex":
+                        verts = np.stack([block[c].astype(np.float64) for c in "xyz"], axis=1)
+                    continue
+                for _ in range(n):       # element with a list property: variable-length records
+                    for pr in props:
+                        if pr[0] == "scalar":
+                            f.read(np.dtype(pr[2]).itemsize)
+                            continue
+                        k = int(np.frombuffer(f.read(np.dtype(pr[2]).itemsize), dtype=end + pr[2])[0])
+                        ids = np.frombuffer(f.read(np.dtype(pr[3]).itemsize * k), dtype=end + pr[3]).astype(np.int64)
+                        if el["name"] == "face":
+                            faces.extend([ids[0], ids[j], ids[j + 1]] for j in range(1, k - 1))
+        if verts is None or not faces:
+            raise ValueError(f"{path}: PLY without vertex/face elements (point clouds go through --input_type pc_normal)")
+        return SimpleMesh(verts, np.asarray(faces, dtype=np.int64))
+
+
 def load_mesh(path):
     if trimesh is not None:
         return trimesh.load(path)
-    if not path.endswith(".obj"):
-        raise ImportError("trimesh is needed to load non-OBJ meshes")
-    return SimpleMesh.load_obj(path)
+    low = path.lower()
+    if low.endswith(".obj"):
+        return SimpleMesh.load_obj(path)
+    if low.endswith(".ply"):
+        return SimpleMesh.load_ply(path)
+    raise ImportError(f"{path}: trimesh is needed to load meshes other than .obj / .ply")
 
 
 def normalize_vertices(vertices, scale=0.9):

@@ -59,3 +59,62 @@ def test_obj_export_merges_vertices_and_faces(tmp_path, monkeypatch):
     txt = path.read_text().splitlines()
     assert n == 2 and sum(l.startswith("f ") for l in txt) == 2
     assert sum(l.startswith("v ") for l in txt) == 4                            # 9 corners -> 4 distinct vertices
+
+
+def _cube():
+    v = np.array([[x, y, z] for x in (0, 1) for y in (0, 1) for z in (0, 1)], dtype=np.float32)
+    quads = [[0, 1, 3, 2], [4, 6, 7, 5], [0, 4, 5, 1], [2, 3, 7, 6], [0, 2, 6, 4], [1, 5, 7, 3]]
+    return v, quads
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary_little_endian", "binary_big_endian"])
+def test_numpy_ply_loader(tmp_path, fmt):
+    """PLY without trimesh: ascii / binary, extra vertex properties, quads fan-triangulated, a skipped extra element."""
+    import struct
+    import mesh_to_pc
+    v, quads = _cube()
+    path = tmp_path / f"cube_{fmt}.ply"
+    header = (f"ply\nformat {fmt} 1.0\ncomment made by a test\nelement vertex 8\nproperty float x\nproperty float y\n"
+              "property float z\nproperty uchar red\nproperty double quality\nelement face 6\n"
+              "property list uchar int vertex_indices\nelement edge 1\nproperty int vertex1\nproperty int vertex2\n"
+              "end_header\n")
+    with open(path, "wb") as f:
+        f.write(header.encode())
+        if fmt == "ascii":
+            for p in v:
+                f.write(f"{p[0]} {p[1]} {p[2]} 200 0.5\n".encode())
+            for q in quads:
+                f.write(("4 " + " ".join(map(str, q)) + "\n").encode())
+            f.write(b"0 1\n")
+        else:
+            e = "<" if fmt == "binary_little_endian" else ">"
+            for p in v:
+                f.write(struct.pack(e + "fffBd", p[0], p[1], p[2], 200, 0.5))
+            for q in quads:
+                f.write(struct.pack(e + "Biiii", 4, *q))
+            f.write(struct.pack(e + "ii", 0, 1))
+    m = mesh_to_pc.SimpleMesh.load_ply(str(path))
+    assert m.vertices.shape == (8, 3) and m.faces.shape == (12, 3)
+    assert np.allclose(m.vertices, v)
+    t = m.vertices[m.faces]
+    area = 0.5 * np.linalg.norm(np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0]), axis=1).sum()
+    assert abs(area - 6.0) < 1e-9                      # the cube's surface, whatever the triangulation
+    if mesh_to_pc.trimesh is None:
+        pcs, _ = mesh_to_pc.process_mesh_to_pc([mesh_to_pc.load_mesh(str(path))])
+        assert pcs[0].shape == (4096, 6)
+
+
+def test_ply_errors(tmp_path):
+    import mesh_to_pc
+    bad = tmp_path / "x.ply"
+    bad.write_bytes(b"plx\n")
+    with pytest.raises(ValueError):
+        mesh_to_pc.SimpleMesh.load_ply(str(bad))
+    cloud = tmp_path / "cloud.ply"
+    cloud.write_bytes(b"ply\nformat ascii 1.0\nelement vertex 1\nproperty float x\nproperty float y\nproperty float z\n"
+                      b"end_header\n0 0 0\n")
+    with pytest.raises(ValueError):
+        mesh_to_pc.SimpleMesh.load_ply(str(cloud))
+    if mesh_to_pc.trimesh is None:
+        with pytest.raises(ImportError):
+            mesh_to_pc.load_mesh(str(tmp_path / "m.stl"))
