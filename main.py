@@ -100,8 +100,56 @@ def load_model(args, device=None):
     return model
 
 
+def fix_winding(vertices, tri):
+    """What `trimesh.Trimesh.fix_normals` does to the faces (main.py:166 of the reference), in numpy: make the winding
+    consistent across every shared edge (breadth-first over face adjacency), then flip each connected component whose
+    signed volume is negative so that normals point outwards."""
+    tri = np.array(tri, dtype=np.int64, copy=True)
+    nf = len(tri)
+    if nf == 0:
+        return tri
+    # undirected edge -> faces that use it, with the direction each face traverses it in
+    edges = {}
+    for f in range(nf):
+        for k in range(3):
+            a, b = int(tri[f, k]), int(tri[f, (k + 1) % 3])
+            if a != b:
+                edges.setdefault((min(a, b), max(a, b)), []).append((f, a < b))
+    adj = [[] for _ in range(nf)]
+    for users in edges.values():
+        if len(users) == 2:                       # manifold edge: consistent iff traversed in opposite directions
+            (f0, d0), (f1, d1) = users
+            adj[f0].append((f1, d0 == d1))
+            adj[f1].append((f0, d0 == d1))
+    comp = -np.ones(nf, dtype=np.int64)
+    flip = np.zeros(nf, dtype=bool)
+    ncomp = 0
+    for seed in range(nf):
+        if comp[seed] >= 0:
+            continue
+        comp[seed] = ncomp
+        queue = [seed]
+        while queue:
+            f = queue.pop()
+            for g, same_dir in adj[f]:
+                if comp[g] < 0:
+                    comp[g] = ncomp
+                    flip[g] = flip[f] ^ same_dir     # same direction on the shared edge = opposite orientation
+                    queue.append(g)
+        ncomp += 1
+    tri[flip] = tri[flip][:, ::-1]
+    t = np.asarray(vertices, dtype=np.float64)[tri]
+    vol6 = np.einsum("ij,ij->i", t[:, 0], np.cross(t[:, 1], t[:, 2]))
+    for c in range(ncomp):
+        sel = comp == c
+        if vol6[sel].sum() < 0:
+            tri[sel] = tri[sel][:, ::-1]
+    return tri
+
+
 def export_obj(path, faces_xyz):
-    """merge_vertices + unique_faces + orange face colour of main.py:161-174 (trimesh when available)."""
+    """merge_vertices + unique_faces + fix_normals + orange face colour of main.py:161-174 (trimesh when available,
+    the numpy equivalents otherwise)."""
     vertices = faces_xyz.reshape(-1, 3)
     triangles = np.arange(len(vertices)).reshape(-1, 3)
     try:
@@ -117,7 +165,7 @@ def export_obj(path, faces_xyz):
         uniq, inv = np.unique(np.round(vertices, 8), axis=0, return_inverse=True)
         tri = inv.reshape(-1)[triangles]
         _, keep = np.unique(np.sort(tri, axis=1), axis=0, return_index=True)
-        tri = tri[np.sort(keep)]
+        tri = fix_winding(uniq, tri[np.sort(keep)])
         with open(path, "w") as f:
             for v in uniq:
                 f.write(f"v {v[0]:.8f} {v[1]:.8f} {v[2]:.8f} 1.00000000 0.64705882 0.00000000\n")

@@ -118,3 +118,38 @@ def test_ply_errors(tmp_path):
     if mesh_to_pc.trimesh is None:
         with pytest.raises(ImportError):
             mesh_to_pc.load_mesh(str(tmp_path / "m.stl"))
+
+
+def test_fix_winding_orients_a_scrambled_cube_outwards():
+    import main
+    v, quads = _cube()
+    tri = []
+    for q in quads:
+        tri += [[q[0], q[1], q[2]], [q[0], q[2], q[3]]]
+    tri = np.array(tri)
+    rng = np.random.default_rng(0)
+    scrambled = tri.copy()
+    flipped = rng.random(len(tri)) < 0.5
+    scrambled[flipped] = scrambled[flipped][:, ::-1]
+    # two cubes far apart = two components, the second one entirely inside-out
+    v2 = np.concatenate([v, v + 10.0])
+    tri2 = np.concatenate([scrambled, tri[:, ::-1] + 8])
+    fixed = main.fix_winding(v2, tri2)
+    assert sorted(map(tuple, np.sort(fixed, axis=1))) == sorted(map(tuple, np.sort(tri2, axis=1)))   # same faces
+    t = v2[fixed].astype(np.float64)
+    n = np.cross(t[:, 1] - t[:, 0], t[:, 2] - t[:, 0])
+    centre = np.where((np.arange(len(fixed)) < len(tri))[:, None], v.mean(0), v.mean(0) + 10.0)
+    assert (np.einsum("ij,ij->i", n, t.mean(1) - centre) > 0).all()          # every normal points away from its cube
+
+
+def test_export_obj_merges_vertices_and_drops_duplicate_faces(tmp_path):
+    import main
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]],
+                    [[1, 0, 0], [1, 1, 0], [0, 1, 0]],
+                    [[0, 1, 0], [0, 0, 0], [1, 0, 0]]], dtype=np.float32)       # third = first, rotated
+    path = tmp_path / "m.obj"
+    n = main.export_obj(str(path), tri)
+    txt = path.read_text().splitlines()
+    vs = [l for l in txt if l.startswith("v ")]
+    fs = [l for l in txt if l.startswith("f ")]
+    assert n == 2 and len(fs) == 2 and len(vs) == 4
