@@ -14,6 +14,10 @@ LIB = os.path.join(LIB_DIR, "libmeshanything_b200.so")
 SOURCES = ["gemm_canon.cu", "attention.cu", "elementwise.cu", "decode_fast.cu", "decode_mega.cu", "api.cu", "glue.cu", "gemm_tc.cu", "attention_tc.cu", "api_encoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+if os.environ.get("MA_B200_FHFMA") == "1":
+    # opt-in: canonical dot products on the mixed-precision FMA (SASS FHFMA) instead of convert + FFMA; same values by
+    # construction, kept off until the bit-exact GPU suite has run with it (rebuild with MA_B200_REBUILD=1)
+    NVCC_FLAGS.append("-DMA_FHFMA")
 
 
 def _nvcc() -> str:

@@ -47,6 +47,27 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   }
 }
 
+#ifdef MA_FHFMA
+// Mixed-precision FMA of sm_100 (PTX fma.rn.f32.f16 -> SASS FHFMA, operands taken straight from the packed halves with
+// .H0/.H1 selectors): d = float(a) * float(b) + c with ONE rounding -- the same value as ffma(unpacked a, unpacked b, c),
+// because fp16 -> fp32 is exact -- without the 2 conversion instructions per product.  Opt-in (-DMA_FHFMA, build.py:
+// MA_B200_FHFMA=1) until the bit-exact suite has been run with it on hardware.
+__device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
+  asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
+  return c;
+}
+// acc + sum_j w[j] * x[j], j = 0..7 in this order (the canonical per-lane order), on two 16-byte groups of packed halves
+__device__ __forceinline__ float dot8_packed(const uint4& w, const uint4& x, float acc) {
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w}, xw[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    acc = fhfma((unsigned short)(ww[i] & 0xffffu), (unsigned short)(xw[i] & 0xffffu), acc);
+    acc = fhfma((unsigned short)(ww[i] >> 16), (unsigned short)(xw[i] >> 16), acc);
+  }
+  return acc;
+}
+#endif
+
 __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -41,6 +41,32 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32)
   // is multiplied (x right after its conversion, each weight row right after its own conversion), so a warp hides
   // its own load latency -- at small M there are fewer than two warps per scheduler to hide it otherwise.
   const int G = K >> 8;
+#ifdef MA_FHFMA
+  // FHFMA: operands stay packed (no fp16 -> fp32 conversions, half the registers for x); always software-pipelined
+  {
+    uint4 xn[T], wn[R];
+#pragma unroll
+    for (int t = 0; t < T; t++) xn[t] = *reinterpret_cast<const uint4*>(x + xoff[t]);
+#pragma unroll
+    for (int r = 0; r < R; r++) wn[r] = ldg_nc16(W + woff[r]);
+    for (int g = 0; g < G; g++) {
+      const int gn = 256 * min(g + 1, G - 1);
+      uint4 xc[T];
+#pragma unroll
+      for (int t = 0; t < T; t++) {
+        xc[t] = xn[t];
+        xn[t] = *reinterpret_cast<const uint4*>(x + xoff[t] + gn);
+      }
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const uint4 wc = wn[r];
+        wn[r] = ldg_nc16(W + woff[r] + gn);
+#pragma unroll
+        for (int t = 0; t < T; t++) acc[r * T + t] = dot8_packed(wc, xc[t], acc[r * T + t]);
+      }
+    }
+  }
+#else
   if constexpr (PIPE) {
     uint4 xr[T], wr[R];
 #pragma unroll
@@ -93,6 +119,7 @@ __global__ void __launch_bounds__(GEMM_WARPS * 32)
     }
   }
 
+#endif
   // accumulator index a = r*T + t ; after the transposing butterfly lane l holds accumulator 32*s + l
 #pragma unroll
   for (int s = 0; s < (R * T) / 32; s++) {
