@@ -10,13 +10,15 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIB_DIR, "libmeshanything_b200.so")
+# MA_B200_FHFMA=1 selects the opt-in variant (own file names, so both builds travel to the GPU box side by side)
+VARIANT = "_fhfma" if os.environ.get("MA_B200_FHFMA") == "1" else ""
+LIB = os.path.join(LIB_DIR, f"libmeshanything_b200{VARIANT}.so")
 SOURCES = ["gemm_canon.cu", "attention.cu", "elementwise.cu", "decode_fast.cu", "decode_mega.cu", "api.cu", "glue.cu", "gemm_tc.cu", "attention_tc.cu", "api_encoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-if os.environ.get("MA_B200_FHFMA") == "1":
+if VARIANT:
     # opt-in: canonical dot products on the mixed-precision FMA (SASS FHFMA) instead of convert + FFMA; same values by
-    # construction, kept off until the bit-exact GPU suite has run with it (rebuild with MA_B200_REBUILD=1)
+    # construction, kept off until the bit-exact GPU suite has run with it
     NVCC_FLAGS.append("-DMA_FHFMA")
 
 
@@ -47,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(LIB_DIR, src.replace(".cu", f"{VARIANT}.o"))
         cmd = [nvcc, *NVCC_FLAGS, "-ccbin", "g++", "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
