@@ -527,12 +527,21 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
           }
         }
         // q of this head and, for the chunk that holds it, k / v of the current token: flagged words
+#ifdef MA_FHFMA
+        uint4 qp;   // q stays packed: the products below are FHFMAs on packed halves
+        {
+          uint2 d[2];
+          ll_wait_units<2>(ws->qkv_w + (h * HD + 8 * li) / 2, 1, ep, d, err);
+          qp = make_uint4(d[0].x, d[0].y, d[1].x, d[1].y);
+        }
+#else
         float qf[8];
         {
           uint2 d[2];
           ll_wait_units<2>(ws->qkv_w + (h * HD + 8 * li) / 2, 1, ep, d, err);
           unpack8(make_uint4(d[0].x, d[0].y, d[1].x, d[1].y), qf);
         }
+#endif
         if (cur >= 0 && cur < MA_ATTN_CHUNK) {
           const int rho_c = cur >> 5, gl_c = cur & 31;
           if (4 * wt + grp == gl_c) {
@@ -553,11 +562,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
 #pragma unroll
         for (int rho = 0; rho < 8; rho++) {
           const int r = 32 * rho + 4 * wt + grp;
+#ifdef MA_FHFMA
+          float p = dot8_packed(qp, kreg[rho], 0.0f);
+#else
           float kf[8];
           unpack8(kreg[rho], kf);
           float p = 0.0f;
 #pragma unroll
           for (int j = 0; j < 8; j++) p = ffma(qf[j], kf[j], p);
+#endif
           p = fadd(p, __shfl_xor_sync(0xffffffffu, p, 4));
           p = fadd(p, __shfl_xor_sync(0xffffffffu, p, 2));
           p = fadd(p, __shfl_xor_sync(0xffffffffu, p, 1));
@@ -580,11 +593,21 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
           if (r < len) {
             const float e = ma_exp(fsub(sreg[rho], cmax));
             l = fadd(l, e);
+#ifdef MA_FHFMA
+            const unsigned short ph = __half_as_ushort(__float2half_rn(e));
+            const uint32_t vw[4] = {vreg[rho].x, vreg[rho].y, vreg[rho].z, vreg[rho].w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              o[2 * i] = fhfma(ph, (unsigned short)(vw[i] & 0xffffu), o[2 * i]);
+              o[2 * i + 1] = fhfma(ph, (unsigned short)(vw[i] >> 16), o[2 * i + 1]);
+            }
+#else
             const float pf = __half2float(__float2half_rn(e));
             float vf[8];
             unpack8(vreg[rho], vf);
 #pragma unroll
             for (int j = 0; j < 8; j++) o[j] = ffma(pf, vf[j], o[j]);
+#endif
           }
         }
         l = fadd(l, __shfl_xor_sync(0xffffffffu, l, 16));
