@@ -220,3 +220,30 @@ def test_main_cli_continuous_batching(tmp_path):
         assert [os.path.basename(o) for o in objs] == ["s0_gen.obj", "s1_gen.obj", "s2_gen.obj"]
         texts.append([open(o).read() for o in objs])
     assert texts[0] == texts[1]
+
+
+@gpu
+def test_kernel_selections_all_meet_the_tolerance(full):
+    """ma_set_tensor_cores 0 (canonical CUDA-core kernels), 1 (tcgen05 GEMMs, canonical attention) and 2 (default):
+    every selection stays inside the stated encoder tolerance, and they agree with each other to fp16 noise."""
+    from meshanything_b200 import capi
+    from meshanything_b200.encoder import EncoderArena
+    from oracle import torch_ref
+    pc = synthetic_pc_normal(1, first=4)
+    enc = EncoderArena(full, _dev())
+    with torch.no_grad():
+        rpf, rprefix = torch_ref.encoder_forward(full, pc)
+    outs = {}
+    old = capi.lib().ma_set_tensor_cores(2)
+    try:
+        for mode in (0, 1, 2):
+            capi.lib().ma_set_tensor_cores(mode)
+            pf, prefix = enc.forward(pc.to(_dev()))
+            outs[mode] = pf.cpu()
+            d1, d2 = (pf.cpu() - rpf).abs(), (prefix.cpu() - rprefix).abs()
+            print("mode %d: point_feature err max %.4g ; prefix err max %.4g" % (mode, d1.max(), d2.max()))
+            assert d1.max() < TOL_PF_MAX and d1.mean() < TOL_PF_MEAN, mode
+            assert d2.max() < TOL_PREFIX_MAX and d2.mean() < TOL_PREFIX_MEAN, mode
+    finally:
+        capi.lib().ma_set_tensor_cores(old)
+    assert (outs[0] - outs[2]).abs().max() < 2 * TOL_PF_MAX and (outs[1] - outs[2]).abs().max() < 2 * TOL_PF_MAX
