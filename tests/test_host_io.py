@@ -153,3 +153,35 @@ def test_export_obj_merges_vertices_and_drops_duplicate_faces(tmp_path):
     vs = [l for l in txt if l.startswith("v ")]
     fs = [l for l in txt if l.startswith("f ")]
     assert n == 2 and len(fs) == 2 and len(vs) == 4
+
+
+def test_dataset_from_mesh_files(tmp_path):
+    """main.Dataset('mesh', [...]) on an OBJ and a PLY file (reference main.py:15-58): 4096 points, max |x| = 0.9995,
+    unit normals, fp16."""
+    import main
+    import mesh_to_pc
+    if mesh_to_pc.trimesh is not None:
+        pytest.skip("exercises the numpy readers")
+    v, quads = _cube()
+    obj = tmp_path / "cube.obj"
+    with open(obj, "w") as f:
+        for p in v:
+            f.write(f"v {p[0]} {p[1]} {p[2]}\n")
+        for q in quads:
+            f.write("f " + " ".join(str(i + 1) for i in q) + "\n")
+    ply = tmp_path / "cube2.ply"
+    with open(ply, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex 8\nproperty float x\nproperty float y\nproperty float z\n"
+                "element face 6\nproperty list uchar int vertex_indices\nend_header\n")
+        for p in v:
+            f.write(f"{p[0] * 3} {p[1] * 3} {p[2] * 3}\n")
+        for q in quads:
+            f.write("4 " + " ".join(map(str, q)) + "\n")
+    np.random.seed(0)
+    ds = main.Dataset("mesh", [str(obj), str(ply)])
+    assert len(ds) == 2 and [ds.data[i]["uid"] for i in range(2)] == ["cube", "cube2"]
+    for i in range(2):
+        pc = ds[i]["pc_normal"]
+        assert pc.shape == (4096, 6) and pc.dtype == np.float16
+        assert abs(np.abs(pc[:, :3].astype(np.float32)).max() - 0.9995) < 2e-3
+        assert np.allclose(np.linalg.norm(pc[:, 3:].astype(np.float32), axis=1), 1.0, atol=5e-3)
