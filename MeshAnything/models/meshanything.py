@@ -101,7 +101,9 @@ class MeshAnything(nn.Module):
                                   seed=self.seed + self._calls, eos_id=self.eos_token_id, pad_id=self.pad_token_id)
         self._calls += 1
         self.last_ids = ids
-        return self._tok.detokenize(ids, point_feature, self.n_max_triangles)
+        out = self._tok.detokenize(ids, point_feature, self.n_max_triangles)
+        gen.check()   # a timed-out hand-off inside the persistent decode kernel is an error, never a wrong mesh
+        return out
 
     # ------------------------------------------------------------------ queue of shapes (continuous batching)
     @torch.no_grad()

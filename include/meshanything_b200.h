@@ -30,6 +30,10 @@ extern "C" {
 #define MA_EPI_NONE 0
 #define MA_EPI_RELU 1 /* OPTDecoderLayer activation_fn (opt-350m: relu) */
 #define MA_EPI_GELU 2 /* nn.GELU() exact erf: transformer_blocks.py:239, BERT intermediate */
+/* OR-ed into `epilogue`: the segmented accumulation order of the decoder's split-K layers:
+ * 16 segment dots (64-wide: out_proj, K = 1024; 256-wide: fc2, K = 4096) added with a balanced tree. */
+#define MA_LIN_SEG64 0x10
+#define MA_LIN_SEG256 0x20
 
 int ma_abi_version(void);
 const char* ma_last_error(void);
@@ -144,9 +148,13 @@ int ma_decode_slots_poll(int B, int tmax, void* ws, int32_t* finished_host, int3
 #define MA_GEN_NO_MEGA 16    /* batch-1 greedy: per-phase kernels (decode_fast.cu) instead of the persistent kernel */
 #define MA_GEN_TRACE 32      /* persistent kernel records globaltimer stamps of CTA 0 at every phase boundary */
 
-/* Debug read-back (synchronises the device): what = 0 -> int error flag of the persistent kernel (1 = a grid
- * barrier timed out), what = 1 -> its uint64 trace stamps. */
+/* Debug read-back (synchronises the device): what = 0 -> int error flag of the persistent kernel (non-zero: a
+ * hand-off timed out; low byte = which wait, next bytes = the CTA), what = 1 -> its uint64 trace stamps, what = 2 ->
+ * the per-CTA stamps.  A time-out also makes the kernel stop emitting tokens and set out_lens[0] = -1. */
 int ma_decoder_debug(void* ws, int B, int tmax, int what, void* host_out, int nbytes);
+/* Test hook of the persistent kernel: bound of every in-kernel wait in ns (0 = keep; default 2 s) and fault injection
+ * (fault = c + 1: CTA c withholds its out_proj partials from the third token on, so the hand-off times out). */
+void ma_mega_set_debug(unsigned long long timeout_ns, int fault);
 
 
 /* Same contract as ma_linear_f16 on the tcgen05 tensor cores (TMA-fed, accumulator in TMEM): fp16 in, fp32

@@ -10,16 +10,15 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-# MA_B200_FHFMA=1 selects the opt-in variant (own file names, so both builds travel to the GPU box side by side)
-VARIANT = "_fhfma" if os.environ.get("MA_B200_FHFMA") == "1" else ""
+# MA_B200_NO_FHFMA=1 selects the convert + FFMA variant of the canonical dot products (own file names, so both builds
+# travel to the GPU box side by side); the default uses the mixed-precision FMA (SASS FHFMA), see canon.cuh
+VARIANT = "_nofhfma" if os.environ.get("MA_B200_NO_FHFMA") == "1" else ""
 LIB = os.path.join(LIB_DIR, f"libmeshanything_b200{VARIANT}.so")
 SOURCES = ["gemm_canon.cu", "attention.cu", "elementwise.cu", "decode_fast.cu", "decode_mega.cu", "api.cu", "glue.cu", "gemm_tc.cu", "attention_tc.cu", "api_encoder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 if VARIANT:
-    # opt-in: canonical dot products on the mixed-precision FMA (SASS FHFMA) instead of convert + FFMA; same values by
-    # construction, kept off until the bit-exact GPU suite has run with it
-    NVCC_FLAGS.append("-DMA_FHFMA")
+    NVCC_FLAGS.append("-DMA_NO_FHFMA")
 
 
 def _nvcc() -> str:
@@ -27,6 +26,10 @@ def _nvcc() -> str:
         if c and os.path.exists(c):
             return c
     raise RuntimeError("nvcc not found")
+
+
+def have_nvcc() -> bool:
+    return bool(shutil.which("nvcc")) or os.path.exists("/usr/local/cuda/bin/nvcc")
 
 
 def _stale() -> bool:

@@ -15,6 +15,7 @@ from . import build as _build
 
 MA_MAX_LAYERS = 32
 EPI_NONE, EPI_RELU, EPI_GELU = 0, 1, 2
+LIN_SEG64, LIN_SEG256 = 0x10, 0x20   # OR-ed into the epilogue: segmented order of the decoder's out_proj / fc2
 GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT, GEN_NO_MEGA, GEN_TRACE = 1, 2, 4, 8, 16, 32
 
 _vp = C.c_void_p
@@ -42,6 +43,7 @@ EXPORTS = [
     "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores", "ma_sample_tokens",
     "ma_attention_tc_f16", "ma_transpose_heads_f16",
     "ma_decode_slots_init", "ma_decode_slot_prefill", "ma_decode_slots_step", "ma_decode_slots_poll",
+    "ma_mega_set_debug",
 ]
 
 
@@ -55,8 +57,13 @@ def lib():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path) or (os.environ.get("MA_B200_REBUILD") == "1"):
-        path = _build.build()
+    # rebuild when the library is older than its sources -- in a development checkout only (.git present, nvcc
+    # available): the GPU box gets the prebuilt file with a snapshot whose mtimes are those of the copy
+    dev_tree = os.path.isdir(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".git"))
+    stale = (os.path.exists(path) and dev_tree and _build.have_nvcc()
+             and os.environ.get("MA_B200_NO_AUTOBUILD") != "1" and _build._stale())
+    if not os.path.exists(path) or stale or (os.environ.get("MA_B200_REBUILD") == "1"):
+        path = _build.build(force=True)
     L = C.CDLL(path)
     L.ma_abi_version.restype = C.c_int
     L.ma_last_error.restype = C.c_char_p
@@ -84,6 +91,8 @@ def lib():
                                        C.POINTER(Sampling), C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]
     L.ma_decode_slots_poll.argtypes = [C.c_int, C.c_int, _vp, _vp, _vp, _vp]
     L.ma_decoder_debug.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_int]
+    L.ma_mega_set_debug.argtypes = [C.c_ulonglong, C.c_int]
+    L.ma_mega_set_debug.restype = None
     L.ma_encoder_workspace_bytes.argtypes = [C.c_int]
     L.ma_encoder_workspace_bytes.restype = C.c_size_t
     L.ma_encoder_forward.argtypes = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]

@@ -105,12 +105,12 @@ static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, in
     if (launch_attention(ws.qkv, QKV, kc, vc, T, NHEAD, rows_per_slot, nullptr, ws.nkeys, max_keys, M, 0.125f,
                          ws.attn16, HID, scratch, st)) return 1;
     if (launch_linear((const __half*)w->wo[L], (const __half*)w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID,
-                      MA_EPI_NONE, st)) return 1;
+                      MA_EPI_NONE | MA_LIN_SEG64, st)) return 1;   // split-K by head (canonical order)
     if (launch_layernorm(ws.hres, ws.y16, w->ln1g[L], w->ln1b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
     if (launch_linear((const __half*)w->w1[L], (const __half*)w->b1[L], ws.x16, HID, ws.f16, FFN, M, FFN, HID,
                       MA_EPI_RELU, st)) return 1;
     if (launch_linear((const __half*)w->w2[L], (const __half*)w->b2[L], ws.f16, FFN, ws.y16, HID, M, HID, FFN,
-                      MA_EPI_NONE, st)) return 1;
+                      MA_EPI_NONE | MA_LIN_SEG256, st)) return 1;  // split-K by 256 fc1 rows
     if (launch_layernorm(ws.hres, ws.y16, w->ln2g[L], w->ln2b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
   }
   return 0;
@@ -334,12 +334,10 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   sa.all_done = ws.all_done;
 
   const bool fast = (B == 1) && !(flags & MA_GEN_NO_FAST);
-  const bool mega = fast && !sa.do_sample && !(flags & MA_GEN_NO_MEGA);
+  // the persistent kernel needs 144 co-resident CTAs and tmax <= 15360 keys; otherwise the per-phase kernels run
+  bool mega = fast && !sa.do_sample && !(flags & MA_GEN_NO_MEGA) && mega_fits(tmax) && mega_supported();
   if (fast) sa.nkeys_next = fast_nkeys_ptr(ws.fast);
-  if (mega && mega_prepare(w, ws.mega, st)) {
-    set_error("mega_prepare failed");
-    return 1;
-  }
+  if (mega && mega_prepare(w, ws.mega, st)) mega = false;   // (message kept in ma_last_error)
 
   // ---- prefill: 257 prefix rows per sequence, PREFILL_SEQS sequences per pass
   for (int b0 = 0; b0 < B; b0 += PREFILL_SEQS) {
@@ -530,6 +528,8 @@ int ma_decode_slots_poll(int B, int tmax, void* ws_, int32_t* finished_host, int
   return slots_leave(stream, "ma_decode_slots_poll");
 }
 
+
+void ma_mega_set_debug(unsigned long long timeout_ns, int fault) { mega_set_debug(timeout_ns, fault); }
 
 int ma_decoder_debug(void* ws_, int B, int tmax, int what, void* host_out, int nbytes) {
   DecWs ws = carve(ws_, B, tmax, 8195 + 61);

@@ -47,11 +47,19 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   }
 }
 
-#ifdef MA_FHFMA
 // Mixed-precision FMA of sm_100 (PTX fma.rn.f32.f16 -> SASS FHFMA, operands taken straight from the packed halves with
 // .H0/.H1 selectors): d = float(a) * float(b) + c with ONE rounding -- the same value as ffma(unpacked a, unpacked b, c),
-// because fp16 -> fp32 is exact -- without the 2 conversion instructions per product.  Opt-in (-DMA_FHFMA, build.py:
-// MA_B200_FHFMA=1) until the bit-exact suite has been run with it on hardware.
+// because fp16 -> fp32 is exact -- without the 2 conversion instructions per product.  Checked on the B200 against
+// convert + FFMA on 67 M random products incl. subnormal, inf and nan inputs: 0 mismatches
+// (tools/microbench_cluster.cu, profiles/microbench_cluster_r02.txt), and by the bit-exact GPU suite against the CPU
+// oracle.  Default since round 2; -DMA_NO_FHFMA (build.py: MA_B200_NO_FHFMA=1) builds the convert + FFMA variant.
+#ifndef MA_NO_FHFMA
+#ifndef MA_FHFMA
+#define MA_FHFMA 1
+#endif
+#endif
+
+#ifdef MA_FHFMA
 __device__ __forceinline__ float fhfma(unsigned short a, unsigned short b, float c) {
   asm("fma.rn.f32.f16 %0, %1, %2, %0;" : "+f"(c) : "h"(a), "h"(b));
   return c;
@@ -67,6 +75,38 @@ __device__ __forceinline__ float dot8_packed(const uint4& w, const uint4& x, flo
   return acc;
 }
 #endif
+
+// acc + sum_j w[j] * x[j], j = 0..7 sequentially (the canonical per-lane chain); either build gives the same bits
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
+#ifdef MA_FHFMA
+  return dot8_packed(w, x, acc);
+#else
+  float wf[8], xf[8];
+  unpack8(w, wf);
+  unpack8(x, xf);
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc = ffma(wf[j], xf[j], acc);
+  return acc;
+#endif
+}
+// o[j] = float(p) * float(v[j]) + o[j], j = 0..7 (the P.V step of the canonical attention: P already rounded to fp16)
+__device__ __forceinline__ void pv8(__half p, const uint4& v, float* o) {
+#ifdef MA_FHFMA
+  const unsigned short ph = __half_as_ushort(p);
+  const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    o[2 * i] = fhfma(ph, (unsigned short)(vw[i] & 0xffffu), o[2 * i]);
+    o[2 * i + 1] = fhfma(ph, (unsigned short)(vw[i] >> 16), o[2 * i + 1]);
+  }
+#else
+  const float pf = __half2float(p);
+  float vf[8];
+  unpack8(v, vf);
+#pragma unroll
+  for (int j = 0; j < 8; j++) o[j] = ffma(pf, vf[j], o[j]);
+#endif
+}
 
 __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
   uint4 r;
@@ -103,6 +143,63 @@ __device__ __forceinline__ float transpose_reduce32(float* v, int lane) {
     }
   }
   return v[0];
+}
+
+// The same with a chosen lane-bit order.  ORD = 1: xor-4,2,1,8,16 -- the segmented (64-wide) order of the decoder's
+// out_proj: the 8 lanes of a 64-element segment are reduced first, then the 4 segments of the 256-wide group as a
+// balanced tree.  On return lane l holds accumulator transpose_owner<ORD>(l) in v[0].
+template <int ORD>
+__device__ __forceinline__ float transpose_reduce32o(float* v, int lane) {
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    const int s = 16 >> k;
+    const int m = ORD ? (k == 0 ? 4 : k == 1 ? 2 : k == 2 ? 1 : k == 3 ? 8 : 16) : s;
+    const bool up = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < s; i++) {
+      float mine = up ? v[i + s] : v[i];
+      float other = up ? v[i] : v[i + s];
+      float recv = __shfl_xor_sync(0xffffffffu, other, m);
+      v[i] = fadd(mine, recv);
+    }
+  }
+  return v[0];
+}
+template <int ORD>
+__device__ __forceinline__ int transpose_owner(int lane) {
+  if (!ORD) return lane;
+  return ((lane & 4) ? 16 : 0) | ((lane & 2) ? 8 : 0) | ((lane & 1) ? 4 : 0) | ((lane & 8) ? 2 : 0) | ((lane & 16) ? 1 : 0);
+}
+// every lane ends with the xor-4,2,1,8,16 sum (the seg-64 order) of the 32 lane partials
+__device__ __forceinline__ float warp_sum_seg64(float v) {
+  v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  v = fadd(v, __shfl_xor_sync(0xffffffffu, v, 16));
+  return v;
+}
+// balanced binary tree over 16 values in index order, fed one value at a time (g = 0..15); lv = 4 level registers
+__device__ __forceinline__ float tree16_push(float v, int g, float* lv) {
+  if (g & 1) {
+    v = fadd(lv[0], v);
+    if (g & 2) {
+      v = fadd(lv[1], v);
+      if (g & 4) {
+        v = fadd(lv[2], v);
+        if (g & 8) v = fadd(lv[3], v); else lv[3] = v;
+      } else lv[2] = v;
+    } else lv[1] = v;
+  } else lv[0] = v;
+  return v;   // the total after g = 15
+}
+// the same over 4 values (g = 0..3): (v0 + v1) + (v2 + v3); lv = 2 registers
+__device__ __forceinline__ float tree4_push(float v, int g, float* lv) {
+  if (g == 0) lv[0] = v;
+  else if (g == 1) lv[0] = fadd(lv[0], v);
+  else if (g == 2) lv[1] = v;
+  else v = fadd(lv[0], fadd(lv[1], v));
+  return v;   // the total after g = 3
 }
 
 // pairwise left-to-right tree over n (<= 8) warp sums held in shared memory

@@ -95,6 +95,9 @@ size_t mega_workspace_bytes();
 int mega_prepare(const ma_decoder_weights* w, void* mega_ws, cudaStream_t st);
 int mega_enqueue(const ma_decoder_weights* w, SeqState s, int tmax, __half* kv, void* mega_ws, const SampleArgs& sa,
                  int n_steps, int step_base, int trace, cudaStream_t st);
+int mega_supported();          // 1: 144 CTAs of the kernel's shape are co-resident on this device
+bool mega_fits(int tmax);
+void mega_set_debug(unsigned long long timeout_ns, int fault);
 int mega_error_flag_offset();
 int mega_trace_offset();
 int mega_trace_cta_offset();

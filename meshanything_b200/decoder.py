@@ -120,10 +120,21 @@ class Generator:
                                            capi.ptr(ids), capi.ptr(lens), capi.ptr(forced_ids), capi.ptr(logits),
                                            flags, capi.stream_ptr())
         capi.check(rc, "ma_decode_generate")
+        self._last_lens = lens
         return (ids, lens, logits) if want_logits else (ids, lens)
 
+    def check(self):
+        """Raises if the last generate() failed on the device: the persistent decode kernel reports a timed-out
+        hand-off between SMs by writing lens = -1 and emitting no further tokens (synchronises the stream)."""
+        lens = getattr(self, "_last_lens", None)
+        if lens is not None and bool((lens < 0).any().item()):
+            code = self.mega_error()
+            raise RuntimeError(f"ma_decode_generate: the persistent decode kernel timed out waiting for another SM "
+                               f"(wait {code & 0xff}, CTA {code >> 8}); no valid token sequence was produced")
+
     def mega_error(self) -> int:
-        """1 if a grid barrier of the persistent decode kernel timed out (synchronises the device)."""
+        """non-zero if a hand-off of the persistent decode kernel timed out (synchronises the device): low byte =
+        which wait, the rest = the CTA that gave up first."""
         out = C.c_int(0)
         capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 0, C.byref(out), 4),
                    "ma_decoder_debug")
@@ -136,8 +147,8 @@ class Generator:
                    "ma_decoder_debug")
         return list(buf)
 
-    def mega_trace_cta(self, n_cta: int = 147):
-        buf = (C.c_uint64 * (160 * 8))()
-        capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 2, buf, 8 * 160 * 8),
+    def mega_trace_cta(self, n_cta: int = 144, n_stamps: int = 16):
+        buf = (C.c_uint64 * (n_cta * n_stamps))()
+        capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 2, buf, 8 * n_cta * n_stamps),
                    "ma_decoder_debug")
-        return [[buf[c * 8 + k] for k in range(8)] for c in range(n_cta)]
+        return [[buf[c * n_stamps + k] for k in range(n_stamps)] for c in range(n_cta)]

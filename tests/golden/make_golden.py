@@ -101,7 +101,7 @@ def make_decoder():
     print("decoder_hf_fp32.npz", ref.shape)
 
 
-def make_greedy(faces=64, n_layers=24):
+def make_greedy(faces=64, n_layers=24, eos_id=1):
     """greedy ids of the synthetic decoder from the CPU oracle: F=64 is config 1's length (578 tokens), F=800
     config 2's (7202 tokens, contexts up to 7458: ~2.5 minutes of oracle time on 8 cores), F=1600 config 5's
     (14402 tokens, contexts up to 14658 = 58 attention chunks; the first 4 layers only, to bound the oracle time)."""
@@ -110,8 +110,8 @@ def make_greedy(faces=64, n_layers=24):
     n = faces * 9 + 2
     prefix = random_prefix(1, seed=1)[0]
     oracle = OracleDecoder(sd, n_layers, 257 + n)
-    ids, _ = oracle.generate(prefix, n)
-    json.dump({"ids": ids, "n_layers": n_layers, "prefix_seed": 1, "checkpoint_seed": 0, "faces": faces},
+    ids, _ = oracle.generate(prefix, n, eos_id=eos_id)
+    json.dump({"ids": ids, "n_layers": n_layers, "prefix_seed": 1, "checkpoint_seed": 0, "faces": faces, "eos_id": eos_id},
               open(os.path.join(HERE, f"decoder_greedy_seed0_F{faces}.json"), "w"))
     print(f"decoder_greedy_seed0_F{faces}.json", len(ids), ids[:12], "distinct", len(set(ids)))
 
@@ -125,7 +125,7 @@ if __name__ == "__main__":
     if what in ("greedy800", "all"):
         make_greedy(800)
     if what in ("greedy1600", "all"):
-        make_greedy(1600, n_layers=4)
+        make_greedy(1600, n_layers=4, eos_id=-1)   # length coverage: eos disabled so that all 14402 steps run
     if what in ("encoder", "all"):
         from tests.golden import make_golden_encoder
         make_golden_encoder.main()

@@ -28,6 +28,27 @@ def test_linear_bit_exact(M, N, K, epi):
 
 
 @gpu
+@pytest.mark.parametrize("M,seg", [(1, 64), (3, 64), (9, 64), (64, 64), (257, 64), (1, 256), (5, 256), (64, 256), (257, 256)])
+def test_linear_segmented_bit_exact(M, seg):
+    """The split-K order of the decoder's out_proj (16 segments of 64) / fc2 (16 segments of 256): 16 segment dots,
+    balanced tree (oracle: dot_seg_T).  Every row count takes the same order (batch invariance)."""
+    from meshanything_b200 import capi
+    from oracle import decoder as orc
+    K, N = 16 * seg, 200 if M > 9 else 1024
+    g = torch.Generator().manual_seed(M * 7 + seg)
+    w = (torch.randn(N, K, generator=g) * 0.05).half()
+    b = (torch.randn(N, generator=g) * 0.1).half()
+    x = torch.randn(M, K, generator=g).half()
+    ref = orc.linear(w, b, x, seg=seg)
+    flag = capi.LIN_SEG64 if seg == 64 else capi.LIN_SEG256
+    got = capi.linear_f16(w.to(_dev()), b.to(_dev()), x.to(_dev()), epilogue=flag).cpu()
+    assert torch.equal(got.view(torch.int16), ref.view(torch.int16))
+    # the two orders differ in fp32 rounding only
+    plain = capi.linear_f16(w.to(_dev()), b.to(_dev()), x.to(_dev())).cpu()
+    assert (plain.float() - got.float()).abs().max() <= 2.0 ** -9 * got.float().abs().max() + 1e-3
+
+
+@gpu
 def test_linear_gelu_tolerance():
     from meshanything_b200 import capi
     g = torch.Generator().manual_seed(5)
