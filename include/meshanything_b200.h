@@ -147,6 +147,8 @@ int ma_decode_slots_poll(int B, int tmax, void* ws, int32_t* finished_host, int3
 #define MA_GEN_NO_EARLY_EXIT 8
 #define MA_GEN_NO_MEGA 16    /* batch-1 greedy: per-phase kernels (decode_fast.cu) instead of the persistent kernel */
 #define MA_GEN_TRACE 32      /* persistent kernel records globaltimer stamps of CTA 0 at every phase boundary */
+#define MA_GEN_TRACE_FINE 128 /* MA_GEN_TRACE plus stamps inside the phases (tools/trace_mega.py --fine) */
+#define MA_GEN_WHERE 64      /* debug: every CTA records the last phase it passed (frozen at the first time-out) */
 
 /* Debug read-back (synchronises the device): what = 0 -> int error flag of the persistent kernel (non-zero: a
  * hand-off timed out; low byte = which wait, next bytes = the CTA), what = 1 -> its uint64 trace stamps, what = 2 ->

@@ -16,7 +16,7 @@ from . import build as _build
 MA_MAX_LAYERS = 32
 EPI_NONE, EPI_RELU, EPI_GELU = 0, 1, 2
 LIN_SEG64, LIN_SEG256 = 0x10, 0x20   # OR-ed into the epilogue: segmented order of the decoder's out_proj / fc2
-GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT, GEN_NO_MEGA, GEN_TRACE = 1, 2, 4, 8, 16, 32
+GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT, GEN_NO_MEGA, GEN_TRACE, GEN_WHERE, GEN_TRACE_FINE = 1, 2, 4, 8, 16, 32, 64, 128
 
 _vp = C.c_void_p
 

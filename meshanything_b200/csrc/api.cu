@@ -365,7 +365,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
     const int MEGA_STEPS = 512;
     for (int i = 1; i < max_new && rc == 0; i += MEGA_STEPS) {
       rc = mega_enqueue(w, ws.s, tmax, (__half*)kv, ws.mega, sa, std::min(MEGA_STEPS, max_new - i), i - 1,
-                        (flags & MA_GEN_TRACE) ? 1 : 0, st);
+                        ((flags & MA_GEN_TRACE) ? 1 : 0) | ((flags & MA_GEN_WHERE) ? 2 : 0) | ((flags & MA_GEN_TRACE_FINE) ? 5 : 0), st);
     }
   }
   for (int i = 1; i < max_new && rc == 0 && !mega; i++) {
@@ -532,9 +532,13 @@ int ma_decode_slots_poll(int B, int tmax, void* ws_, int32_t* finished_host, int
 void ma_mega_set_debug(unsigned long long timeout_ns, int fault) { mega_set_debug(timeout_ns, fault); }
 
 int ma_decoder_debug(void* ws_, int B, int tmax, int what, void* host_out, int nbytes) {
+  if (what >= 100) {   // layout query: byte offset of exchange buffer (what - 100) inside the persistent kernel's workspace
+    *(int*)host_out = mega_ws_offset(what - 100);
+    return 0;
+  }
   DecWs ws = carve(ws_, B, tmax, 8195 + 61);
   cudaDeviceSynchronize();
-  const char* src = (const char*)ws.mega + (what == 0 ? mega_error_flag_offset() : what == 1 ? mega_trace_offset() : mega_trace_cta_offset());
+  const char* src = (const char*)ws.mega + (what == 0 ? mega_error_flag_offset() : what == 1 ? mega_trace_offset() : what == 2 ? mega_trace_cta_offset() : what == 3 ? mega_where_offset() : what == 4 ? mega_fail_offset() : mega_wprog_offset());
   return cudaMemcpy(host_out, src, (size_t)nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 

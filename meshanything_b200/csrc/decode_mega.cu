@@ -31,6 +31,8 @@
 //     are prefetched into L2 (cp.async.bulk.prefetch.L2) right after the attention phase of this one.
 // Every wait is bounded (globaltimer deadline): a time-out sets MegaWs::error, the kernel stops emitting tokens and
 // reports lens = -1, which the callers of ma_decode_generate turn into an error (no silently wrong mesh).
+#include <stdlib.h>
+
 #include "canon.cuh"
 #include "internal.h"
 
@@ -77,6 +79,9 @@ struct MegaWs {
   int pad_[3];
   unsigned long long trace[1280];
   unsigned long long trace_cta[MG_GRID * 16];  // per-CTA stamps of one (step, layer): skew analysis
+  int fail[8];                     // first time-out: {code, cta, tid, epoch waited for, epoch seen, word offset in ws, -, -}
+  int wprog[MG_GRID * 16];         // debug (trace & 2): epoch of the last out_proj partial each warp published
+  alignas(16) int where[MG_GRID * 4];   // per CTA: last phase reached {step, layer, phase, -} (post-mortem of a time-out)
   ma_decoder_weights w;             // device copy of the weight table
   alignas(256) __half bias_cta[MA_MAX_LAYERS * MG_GRID * BIAS_N];
   alignas(256) __half wo_p[(size_t)MA_MAX_LAYERS * HID * HID];   // [layer][head][row][64]
@@ -97,6 +102,7 @@ struct MegaArgs {
   int trace;
   int fault;                      // test hook: CTA `fault - 1` withholds its out_proj partials from step 2 on
   unsigned long long timeout_ns;  // bound of every wait
+  unsigned backoff_ns;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -131,14 +137,21 @@ struct WaitCtx {
   int* err;
   unsigned long long timeout_ns;
   int cta;
+  unsigned backoff_ns;   // experiment: sleep between unsuccessful polls (0 = spin)
+  int* fail;
+  const void* base;
 };
 enum { ERR_WBAR = 1, ERR_QKV = 2, ERR_PART = 3, ERR_RED = 4, ERR_Y = 5, ERR_F = 6, ERR_CAND = 7 };
-__device__ __noinline__ bool wait_slow(const WaitCtx& wc, unsigned long long& t0, int code) {
+__device__ __noinline__ bool wait_slow(const WaitCtx& wc, unsigned long long& t0, int code, const void* addr = nullptr,
+                                       uint32_t ep = 0, uint32_t seen = 0) {
   if (ld_volatile_i32(wc.err)) return true;
   const unsigned long long now = gtimer();
   if (t0 == 0) { t0 = now; return false; }
   if (now - t0 > wc.timeout_ns) {
-    atomicCAS(wc.err, 0, code | (wc.cta << 8));
+    if (atomicCAS(wc.err, 0, code | (wc.cta << 8)) == 0) {
+      wc.fail[0] = code; wc.fail[1] = wc.cta; wc.fail[2] = threadIdx.x; wc.fail[3] = (int)ep; wc.fail[4] = (int)seen;
+      wc.fail[5] = addr ? (int)((const char*)addr - (const char*)wc.base) : -1;
+    }
     return true;
   }
   return false;
@@ -181,7 +194,8 @@ __device__ __forceinline__ void ll_wait_words(const uint2* p, long stride, uint3
       }
     }
     if (ok) break;
-    if ((++n & 255u) == 0 && wait_slow(wc, t0, code)) break;
+    if (wc.backoff_ns) __nanosleep(wc.backoff_ns);
+    if ((++n & 255u) == 0 && wait_slow(wc, t0, code, p, ep, w[0].y)) break;
   }
 #pragma unroll
   for (int i = 0; i < N; i++) out[i] = w[i].x;
@@ -205,7 +219,8 @@ __device__ __forceinline__ void ll_wait_units(const uint2* p, uint32_t ep, uint2
       }
     }
     if (ok) break;
-    if ((++n & 255u) == 0 && wait_slow(wc, t0, code)) break;
+    if (wc.backoff_ns) __nanosleep(wc.backoff_ns);
+    if ((++n & 255u) == 0 && wait_slow(wc, t0, code, p, ep, v[0].y != ep ? v[0].y : v[0].w)) break;
   }
 #pragma unroll
   for (int i = 0; i < N; i++) out[i] = make_uint2(v[i].x, v[i].z);
@@ -259,7 +274,9 @@ __device__ __forceinline__ bool last_warp_out(unsigned int* cnt, unsigned nwarps
   bool last = false;
   if (lane == 0) {
     unsigned old;
-    asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+    // relaxed: the shared-memory reads of this warp were issued (in order) before this atomic, and an acq_rel atomic
+    // costs a MEMBAR that also waits for the warp's outstanding GLOBAL stores (the flagged words) -- ~1 us per phase
+    asm volatile("atom.relaxed.cta.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
     last = (old == nwarps - 1);
     if (last) *reinterpret_cast<volatile unsigned int*>(cnt) = 0;
   }
@@ -317,7 +334,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
   const int cta = blockIdx.x;
   const int g = cta / GS;   // group = head = fc1 slice
   const int j = cta % GS;   // rank in the group
-  const WaitCtx wc = {&ws->error, a.timeout_ns, cta};
+  const WaitCtx wc = {&ws->error, a.timeout_ns, cta, a.backoff_ns, ws->fail, ws};
 
   const int NL = ws->w.n_layers, vocab = ws->w.vocab;
   for (int i = tid; i < NL * 6; i += MG_THREADS) {
@@ -399,11 +416,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
 
   // generation state, identical in every CTA
   int pos = a.s.pos[0], gen = a.s.gen[0], tok = a.s.tok[0], fin = a.s.finished[0];
-  unsigned long long* tr = (a.trace && cta == 0 && tid == 0) ? ws->trace : nullptr;
+  unsigned long long* tr = ((a.trace & 1) && cta == 0 && tid == 0) ? ws->trace : nullptr;
   int tri = 0;
 #define STAMP() do { if (tr && tri < 1270) tr[tri++] = gtimer(); } while (0)
+  // trace & 4: additional stamps inside the phases (tools/trace_mega.py --fine)
+#define FSTAMP() do { if (tr && (a.trace & 4) && tri < 1270) tr[tri++] = gtimer(); } while (0)
+  // per-CTA stamps 10..15 of (second traced step, layer NL/2): inside-phase events
+  int cs_L = -1, cs_step = -1;
+#define FCSTAMP(k) do { if ((a.trace & 1) && tid == 0 && cs_step == 1 && cs_L == NL / 2) ws->trace_cta[cta * 16 + (k)] = gtimer(); } while (0)
   // every CTA stamps phase k of (second traced step, layer NL/2)
-#define CSTAMP(k) do { if (a.trace && tid == 0 && step == 1 && L == NL / 2) ws->trace_cta[cta * 16 + (k)] = gtimer(); } while (0)
+  // trace & 2 (debug): every CTA records the last phase it passed, frozen once any wait has timed out
+#define CSTAMP(k) do { if (tid == 0 && a.trace) { \
+      if ((a.trace & 2) && !ld_volatile_i32(&ws->error)) { \
+        volatile int* wh_ = ws->where + 4 * cta; wh_[0] = a.step_base + step + 1; wh_[1] = L; wh_[2] = (k); wh_[3] = lc; } \
+      if ((a.trace & 1) && step == 1 && L == NL / 2) ws->trace_cta[cta * 16 + (k)] = gtimer(); } } while (0)
 
   float hres[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // residual stream: thread t < 256 owns elements 4t..4t+3
 
@@ -416,21 +442,33 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     *reinterpret_cast<uint2*>(sm.xs + 4 * tid) = u;
   };
   // hres <- LN(hres + float(reduced vector words of this thread)), xs <- fp16(hres); all 512 threads call it
+  // debug (trace & 2): lane 0 of every warp records how far it got inside residual_ln (frozen at the first time-out)
+#define WMARK(m) do { if ((a.trace & 2) && lane == 0 && !ld_volatile_i32(&ws->error)) \
+      *reinterpret_cast<volatile int*>(ws->wprog + cta * 16 + warp) = (int)(ep << 8) | (which << 4) | (m); } while (0)
   auto residual_ln = [&](const uint2* words, uint32_t ep, int which) {   // which = 0: ln1, 1: ln2
     const float* lnp = which ? sm.ln2 : sm.ln1;
+    WMARK(1);
     if (tid < 256) {
       uint2 d;
       ll_wait_units<1>(words + 2 * tid, ep, &d, wc, ERR_Y);
+      FSTAMP();
+      FCSTAMP(which ? 14 : 10);
+      WMARK(2);
       const __half2* hh = reinterpret_cast<const __half2*>(&d);
       const float2 p0 = __half22float2(hh[0]), p1 = __half22float2(hh[1]);
       float v[4] = {fadd(hres[0], p0.x), fadd(hres[1], p0.y), fadd(hres[2], p1.x), fadd(hres[3], p1.y)};
       mbar_wait_b(&sm.lnbar[which], PAR(4 + which), wc);
+      FSTAMP();
+      WMARK(3);
       layernorm_1024(v, lnp, lnp + HID, sm.red, tid);
+      WMARK(4);
       hres[0] = v[0]; hres[1] = v[1]; hres[2] = v[2]; hres[3] = v[3];
       publish_x(v);
     }
     FLIP(4 + which);
+    WMARK(5);
     __syncthreads();   // xs complete; every reader of the parameters is done
+    WMARK(6);
   };
   // reducer CTAs: rows 8*cta..8*cta+7 of the 16 partial vectors -> balanced tree, + bias, fp16, 4 flagged words.
   // Thread t < 128: row 8*cta + (t >> 4), partial t & 15; a warp holds the row pair (2*warp, 2*warp + 1).
@@ -462,6 +500,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
     for (int L = 0; L < NL; L++) {
       const uint32_t ep = ep0 + (uint32_t)L;
       const int bsel = lc & 1;
+      cs_L = L; cs_step = step;
       const __half* lb = sm.bias[bsel];
       __half* kc = a.kv + ((size_t)(L * 2 + 0)) * NHEAD * T * HD + (size_t)g * T * HD;   // this head
       __half* vc = a.kv + ((size_t)(L * 2 + 1)) * NHEAD * T * HD + (size_t)g * T * HD;
@@ -519,8 +558,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
       // ---------------- qkv phase: warps 0..n_qp-1 own one row pair each
       mbar_wait_b(&sm.bbar[bsel], PAR(6 + bsel), wc);
       FLIP(6 + bsel);
-      mbar_wait_b(&sm.wbar[0], PAR(0), wc);
+      // Only the warps that read a weight buffer wait for it: a warp that waits without being counted by
+      // last_warp_out could still be waiting for phase p when the refill (phase p + 1) completes, and would then
+      // wait for phase p + 2 forever (parity aliasing).  Every thread flips its parity bit once per phase.
+      if (warp < 11) mbar_wait_b(&sm.wbar[0], PAR(0), wc);
       FLIP(0);
+      FSTAMP();
       if (warp < sm.n_qp) {
         const __half* w2[2] = {bufD + (size_t)(2 * warp) * HID, bufD + (size_t)(2 * warp + 1) * HID};
         float acc[2];
@@ -540,6 +583,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
       if (warp < 11 && last_warp_out(&sm.cnt[0], 11, lane)) {
         if (L + 1 < NL) fill_D(L + 1); else fill_lm(0);
       }
+      // Warps without rows wait HERE (blocked at the barrier) rather than run ahead into the next phase's polls: a
+      // spinning warp shares its scheduler and the SM's load/store pipeline with the warps that still compute, and
+      // was measured to stretch their phase by up to 3x (profiles/mega_trace_r02.txt)
+      __syncthreads();
       STAMP();
       CSTAMP(1);
 
@@ -646,12 +693,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
           }
         }
       }
+      __syncthreads();   // a team without chunks waits here, not in the polls below, while the other team computes
       STAMP();
       CSTAMP(2);
 
       // ---------------- merge of the chunk partials of this head, redundantly in every CTA of the group: all 66 words
       // of every chunk are staged in shared memory by all threads with their polls in flight together; the chunk
       // weights exp(m_c - M) are computed once per chunk; 64 threads run the ascending fma chain of the canonical merge
+#define WMARK2(m) do { if ((a.trace & 2) && lane == 0 && !ld_volatile_i32(&ws->error)) \
+      *reinterpret_cast<volatile int*>(ws->wprog + cta * 16 + warp) = (int)(ep << 8) | (m); } while (0)
+      WMARK2(7);
       {
         const uint2* part = ws->part_w + (long)g * MAX_CHUNKS * PARTF;
         const int nw = nch * PARTF;
@@ -675,6 +726,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
               }
             }
             if (ok) break;
+            if (wc.backoff_ns) __nanosleep(wc.backoff_ns);
             if ((++n & 255u) == 0 && wait_slow(wc, t0, ERR_PART)) break;
           }
 #pragma unroll
@@ -684,12 +736,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
           }
         }
       }
+      FSTAMP();
+      FCSTAMP(15);
+      WMARK2(8);
       __syncthreads();
+      WMARK2(9);
       if (tid < 64) {
         float M = -INFINITY;
         for (int cc = 0; cc < nch; cc++) M = fmaxf(M, sm.part[cc * PARTF + 64]);
         for (int cc = tid; cc < nch; cc += 64) sm.mw[cc] = ma_exp(fsub(sm.part[cc * PARTF + 64], M));
         merge_sync();
+        WMARK2(10);
         float Lsum = 0.0f, O = 0.0f;
         for (int cc = 0; cc < nch; cc++) {
           const float wgt = sm.mw[cc];
@@ -698,13 +755,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         }
         sm.ab[tid] = __float2half_rn(__fdiv_rn(O, Lsum));
       }
+      WMARK2(11);
       __syncthreads();
+      WMARK2(12);
       STAMP();
       CSTAMP(3);
 
       // ---------------- out_proj, split-K by head: this CTA's rows x the 64 columns of head g; one row per 8 lanes
       mbar_wait_b(&sm.wbar[1], PAR(1), wc);
       FLIP(1);
+      FSTAMP();
       {
         const uint4 av = *reinterpret_cast<const uint4*>(sm.ab + 8 * li);
         const bool withhold = a.fault && cta == a.fault - 1 && a.step_base + step >= 2;
@@ -733,8 +793,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
       if (tid == 0) fill_ln((L + 1) % NL, 0);
       STAMP();
       CSTAMP(6);
-      mbar_wait_b(&sm.wbar[2], PAR(2), wc);
+      if (warp < 15) mbar_wait_b(&sm.wbar[2], PAR(2), wc);
       FLIP(2);
+      FSTAMP();
+      FCSTAMP(11);
       if (warp < sm.n_fp) {
         const __half* w2[2] = {bufA + (size_t)(2 * warp) * HID, bufA + (size_t)(2 * warp + 1) * HID};
         float acc[2];
@@ -752,6 +814,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
       if (warp < 15 && last_warp_out(&sm.cnt[2], 15, lane)) {
         if (L + 1 < NL) fill_A(L + 1); else fill_lm(2);
       }
+      __syncthreads();   // as above: nobody polls for the fc1 activations while a warp of this CTA still computes its rows
       STAMP();
       CSTAMP(7);
 
@@ -764,8 +827,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
           ll_wait_units<2>(ws->f_w + g * 128 + 4 * lane, ep, d, wc, ERR_F);
           xr = make_uint4(d[0].x, d[0].y, d[1].x, d[1].y);
         }
+        FSTAMP();
+        FCSTAMP(12);
         mbar_wait_b(&sm.wbar[3], PAR(3), wc);
         FLIP(3);
+        FSTAMP();
+        FCSTAMP(13);
         if (8 * warp < sm.n_sr) {
           float v[8];
 #pragma unroll
@@ -1002,6 +1069,22 @@ int mega_prepare(const ma_decoder_weights* w, void* mega_ws, cudaStream_t st) {
 int mega_error_flag_offset() { return (int)offsetof(MegaWs, error); }
 int mega_trace_offset() { return (int)offsetof(MegaWs, trace); }
 int mega_trace_cta_offset() { return (int)offsetof(MegaWs, trace_cta); }
+int mega_where_offset() { return (int)offsetof(MegaWs, where); }
+int mega_fail_offset() { return (int)offsetof(MegaWs, fail); }
+int mega_wprog_offset() { return (int)offsetof(MegaWs, wprog); }
+int mega_ws_offset(int which) {   // offsets of the exchange buffers (decoding MegaWs::fail[5])
+  switch (which) {
+    case 0: return (int)offsetof(MegaWs, qkv_w);
+    case 1: return (int)offsetof(MegaWs, f_w);
+    case 2: return (int)offsetof(MegaWs, pa_w);
+    case 3: return (int)offsetof(MegaWs, pb_w);
+    case 4: return (int)offsetof(MegaWs, ya_w);
+    case 5: return (int)offsetof(MegaWs, yb_w);
+    case 6: return (int)offsetof(MegaWs, cand_w);
+    case 7: return (int)offsetof(MegaWs, part_w);
+    default: return (int)offsetof(MegaWs, error);
+  }
+}
 
 static unsigned long long g_mega_timeout_ns = 2000000000ull;   // 2 s per wait
 static int g_mega_fault = 0;
@@ -1034,6 +1117,11 @@ int mega_enqueue(const ma_decoder_weights* w, SeqState s, int tmax, __half* kv, 
   a.trace = trace;
   a.fault = g_mega_fault;
   a.timeout_ns = g_mega_timeout_ns;
+  {
+    static int bo = -1;
+    if (bo < 0) { const char* e = getenv("MA_MEGA_BACKOFF_NS"); bo = e ? atoi(e) : 0; }
+    a.backoff_ns = (unsigned)bo;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(MG_GRID);
   cfg.blockDim = dim3(MG_THREADS);

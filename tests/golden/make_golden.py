@@ -101,6 +101,29 @@ def make_decoder():
     print("decoder_hf_fp32.npz", ref.shape)
 
 
+def make_decoder_deep():
+    """decoder_hf_fp32_deep.npz: the same pin at full depth -- 24 layers, 320 teacher-forced positions (contexts 257..576:
+    the second and third 256-key attention chunk), EVERY position stored: fp16 logits of every 8th vocabulary entry
+    (+ the three special tokens), the fp32 argmax and the top-2 values."""
+    from oracle.decoder import OracleDecoder
+    NL, n = 24, 320
+    sd = decoder_sd(NL)
+    prefix = random_prefix(1, seed=4)[0]
+    oracle = OracleDecoder(sd, NL, 257 + n)
+    ids, _ = oracle.generate(prefix, n, eos_id=-1)
+    forced = list(ids)
+    for pos, t in ((5, 0), (6, 1), (7, 2), (100, 1), (255, 2), (256, 0), (300, 1)):   # special-token embeddings, also at
+        forced[pos] = t                                                              # the chunk boundary
+    ref = torch.from_numpy(hf_reference_logits(sd, NL, prefix, forced))
+    cols = sorted(set(range(0, ref.shape[1], 8)) | {0, 1, 2})
+    top2 = torch.topk(ref, 2, dim=1)
+    np.savez_compressed(os.path.join(HERE, "decoder_hf_fp32_deep.npz"), forced=np.asarray(forced, dtype=np.int32),
+                        cols=np.asarray(cols, dtype=np.int32), logits16=ref[:, cols].half().numpy(),
+                        argmax=top2.indices[:, 0].numpy().astype(np.int32), top2=top2.values.numpy().astype(np.float32),
+                        n_layers=NL, prefix_seed=4)
+    print("decoder_hf_fp32_deep.npz", ref.shape, "std", float(ref.std()))
+
+
 def make_greedy(faces=64, n_layers=24, eos_id=1):
     """greedy ids of the synthetic decoder from the CPU oracle: F=64 is config 1's length (578 tokens), F=800
     config 2's (7202 tokens, contexts up to 7458: ~2.5 minutes of oracle time on 8 cores), F=1600 config 5's
@@ -120,6 +143,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("decoder", "all"):
         make_decoder()
+    if what in ("decoder_deep", "all"):
+        make_decoder_deep()
     if what in ("greedy", "all"):
         make_greedy(64)
     if what in ("greedy800", "all"):

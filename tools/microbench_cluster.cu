@@ -160,6 +160,56 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(512, 1) cluster_barr
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = clock64() - t0;
 }
 
+
+// ---- 6. order-free reduction in L2: every CTA adds its partial of every row with ONE 64-bit atomic that carries the
+// fixed-point value (low 48 bits, two's complement) and a contribution count (bits 48..63); every CTA polls the 4
+// rows it needs until the count is complete.  acc has 3 rotating buffers (the one used next is zeroed by its owner).
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+template <int ROWS_PER_CTA>   // 1024: every CTA contributes to every row (fc2); 128: CTA (g, j) to rows 128 j.. (out_proj)
+__global__ void __launch_bounds__(512, 1) exchange_atomic(unsigned long long* acc, int iters, unsigned long long* out) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
+  const int ncontrib = ROWS_PER_CTA == 1024 ? gridDim.x : gridDim.x / 8;
+  unsigned long long t0 = 0;
+  float accf = 0.0f;
+  for (int it = 0; it < iters; it++) {
+    if (it == 10 && tid == 0) t0 = clock64();
+    unsigned long long* a = acc + (size_t)(it % 3) * 1024;
+    unsigned long long* z = acc + (size_t)((it + 1) % 3) * 1024;
+    if (tid < 8) z[(cta % 128) * 8 + tid] = 0ull;   // zero the buffer of the next use (owner: 8 rows per CTA)
+    // contributions: one lane in four holds a row's partial (8 rows per warp instruction)
+    for (int r0 = 0; r0 < ROWS_PER_CTA; r0 += 128) {
+      const int r = r0 + warp * 8 + (lane >> 2);
+      const int row = ROWS_PER_CTA == 1024 ? r : (cta & 7) * 128 + r;
+      const long long fix = __float2ll_rn((float)((row * 7 + cta + it) % 13 - 6 + accf * 1e-20f) * 268435456.0f);
+      if ((lane & 3) == 0) red_add_u64(a + row, (1ull << 48) + (unsigned long long)fix);
+    }
+    // read: thread t < 256 needs rows 4t..4t+3
+    if (tid < 256) {
+      unsigned long long w[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) w[i] = ld_volatile_u64(a + 4 * tid + i);
+      for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if ((int)((w[i] + (1ull << 47)) >> 48) != ncontrib) { ok = false; w[i] = ld_volatile_u64(a + 4 * tid + i); }
+        if (ok) break;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) accf += (float)(long long)(w[i] - ((unsigned long long)ncontrib << 48)) * 3.7252903e-9f;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && cta == 0) { out[0] = clock64() - t0; out[1] = (unsigned long long)accf; }
+}
+
 // compile check only: L2 prefetch of a contiguous range
 __global__ void l2_prefetch_probe(const void* p, unsigned bytes) {
   if (threadIdx.x == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -262,5 +312,19 @@ int main() {
   exchange_full<<<128, 512>>>(part, iters, g_out, 1);  report("  same with injected skew (0.3 us on 1/13 of the CTAs)", iters - 10);
   cudaMemset(part, 0, 8 * 16 * 128 * 8);
   exchange_full<<<8, 512>>>(part, iters, g_out, 0);    report("  same, 1 cluster only (reduce over 1)", iters - 10);
+  unsigned long long* acc;
+  cudaMalloc(&acc, 3 * 1024 * 8);
+  cudaMemset(acc, 0, 3 * 1024 * 8);
+  {
+    void* args[] = {&acc, (void*)&iters, &g_out};
+    cudaLaunchCooperativeKernel((void*)exchange_atomic<1024>, dim3(128), dim3(512), args, 0, 0);
+    report("atomic fixed-point reduce: 128 CTAs x 1024 rows (fc2 shape)", iters - 10);
+    cudaMemset(acc, 0, 3 * 1024 * 8);
+    cudaLaunchCooperativeKernel((void*)exchange_atomic<128>, dim3(128), dim3(512), args, 0, 0);
+    report("atomic fixed-point reduce: 16 contributions per row (out_proj shape)", iters - 10);
+    cudaMemset(acc, 0, 3 * 1024 * 8);
+    cudaLaunchCooperativeKernel((void*)exchange_atomic<1024>, dim3(144), dim3(512), args, 0, 0);
+    report("atomic fixed-point reduce: 144 CTAs x 1024 rows", iters - 10);
+  }
   return 0;
 }

@@ -44,7 +44,10 @@ print(f'layer total {tot:.2f} us; lm+pick {(tr[i] - tr[i - 1]) / 1000.0:.2f} us;
 tc = gen.mega_trace_cta(144)
 import statistics
 base = min(r[0] for r in tc if r[0])
-for k, lab in enumerate(names):
+names2 = names + ['LN1: ya polled', 'fc1: A weights ready', 'fc2: f polled', 'fc2: B weights ready', 'x: yb polled (this layer)', 'merge: parts polled']
+order = [14, 0, 1, 2, 15, 3, 4, 5, 10, 6, 11, 7, 12, 13, 8, 9]
+for k in order:
+    lab = names2[k]
     col = [(r[k] - base) / 1000.0 for r in tc if r[k]]
     srt = sorted(range(len(col)), key=lambda i: col[i])
     print(f'{lab:22s} min {min(col):6.2f} med {statistics.median(col):6.2f} max {max(col):6.2f} us   slowest CTAs {srt[-3:]} fastest {srt[:3]}')
