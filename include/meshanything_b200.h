@@ -132,6 +132,10 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
  *                           synchronising call; the scheduler calls it every few dozen steps).
  * Every sequence gets the ids a solo ma_decode_generate would give it (batch-invariant arithmetic). */
 int ma_decode_slots_init(int B, int tmax, int pad_id, void* ws, void* stream);
+/* Measurement hook (bench.py, tools/): declares every slot live at cached position `pos` having generated `gen` tokens,
+ * last token `tok`, WITHOUT running the steps that lead there -- the KV cache keeps whatever it holds (the caller
+ * zero-fills it).  Lets a bounded number of ma_decode_slots_step calls be timed at a chosen context length. */
+int ma_decode_slots_seek(int B, int tmax, int pos, int gen, int tok, void* ws, void* stream);
 int ma_decode_slot_prefill(const ma_decoder_weights* w, const float* prefix, int slot, int B, int tmax, int max_new,
                            const ma_sampling* sampling, int eos_id, int pad_id, void* kv, void* ws, int32_t* out_ids,
                            void* stream);
@@ -147,15 +151,13 @@ int ma_decode_slots_poll(int B, int tmax, void* ws, int32_t* finished_host, int3
 #define MA_GEN_NO_EARLY_EXIT 8
 #define MA_GEN_NO_MEGA 16    /* batch-1 greedy: per-phase kernels (decode_fast.cu) instead of the persistent kernel */
 #define MA_GEN_TRACE 32      /* persistent kernel records globaltimer stamps of CTA 0 at every phase boundary */
-#define MA_GEN_TRACE_FINE 128 /* MA_GEN_TRACE plus stamps inside the phases (tools/trace_mega.py --fine) */
-#define MA_GEN_WHERE 64      /* debug: every CTA records the last phase it passed (frozen at the first time-out) */
 
-/* Debug read-back (synchronises the device): what = 0 -> int error flag of the persistent kernel (non-zero: a
- * hand-off timed out; low byte = which wait, next bytes = the CTA), what = 1 -> its uint64 trace stamps, what = 2 ->
- * the per-CTA stamps.  A time-out also makes the kernel stop emitting tokens and set out_lens[0] = -1. */
+/* Debug read-back (synchronises the device): what = 0 -> int error word of the persistent kernel (non-zero: a
+ * hand-off between SMs timed out; value = 1 + the CTA that gave up first), what = 1 -> its uint64 trace stamps,
+ * what = 2 -> the per-CTA stamps.  A time-out also makes the kernel stop emitting tokens and set out_lens[0] = -1. */
 int ma_decoder_debug(void* ws, int B, int tmax, int what, void* host_out, int nbytes);
-/* Test hook of the persistent kernel: bound of every in-kernel wait in ns (0 = keep; default 2 s) and fault injection
- * (fault = c + 1: CTA c withholds its out_proj partials from the third token on, so the hand-off times out). */
+/* Test hook of the persistent kernel: bound of every in-kernel wait in ns (0 = keep; default: seconds) and fault
+ * injection (fault = c + 1: CTA c withholds its out_proj rows from the third token on, so the hand-off times out). */
 void ma_mega_set_debug(unsigned long long timeout_ns, int fault);
 
 

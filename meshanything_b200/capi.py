@@ -16,7 +16,7 @@ from . import build as _build
 MA_MAX_LAYERS = 32
 EPI_NONE, EPI_RELU, EPI_GELU = 0, 1, 2
 LIN_SEG64, LIN_SEG256 = 0x10, 0x20   # OR-ed into the epilogue: segmented order of the decoder's out_proj / fc2
-GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT, GEN_NO_MEGA, GEN_TRACE, GEN_WHERE, GEN_TRACE_FINE = 1, 2, 4, 8, 16, 32, 64, 128
+GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT, GEN_NO_MEGA, GEN_TRACE = 1, 2, 4, 8, 16, 32
 
 _vp = C.c_void_p
 
@@ -43,7 +43,7 @@ EXPORTS = [
     "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores", "ma_sample_tokens",
     "ma_attention_tc_f16", "ma_transpose_heads_f16",
     "ma_decode_slots_init", "ma_decode_slot_prefill", "ma_decode_slots_step", "ma_decode_slots_poll",
-    "ma_mega_set_debug",
+    "ma_mega_set_debug", "ma_decode_slots_seek",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
                                       C.c_float, _vp, C.c_int, _vp]
     L.ma_transpose_heads_f16.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _vp, _vp]
     L.ma_decode_slots_init.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.ma_decode_slots_seek.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.ma_decode_slot_prefill.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(Sampling), C.c_int, C.c_int, _vp, _vp, _vp, _vp]
     L.ma_decode_slots_step.argtypes = [C.POINTER(DecoderWeights), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

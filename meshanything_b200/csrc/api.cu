@@ -105,12 +105,12 @@ static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, in
     if (launch_attention(ws.qkv, QKV, kc, vc, T, NHEAD, rows_per_slot, nullptr, ws.nkeys, max_keys, M, 0.125f,
                          ws.attn16, HID, scratch, st)) return 1;
     if (launch_linear((const __half*)w->wo[L], (const __half*)w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID,
-                      MA_EPI_NONE | MA_LIN_SEG64, st)) return 1;   // split-K by head (canonical order)
+                      MA_EPI_NONE, st)) return 1;
     if (launch_layernorm(ws.hres, ws.y16, w->ln1g[L], w->ln1b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
     if (launch_linear((const __half*)w->w1[L], (const __half*)w->b1[L], ws.x16, HID, ws.f16, FFN, M, FFN, HID,
                       MA_EPI_RELU, st)) return 1;
     if (launch_linear((const __half*)w->w2[L], (const __half*)w->b2[L], ws.f16, FFN, ws.y16, HID, M, HID, FFN,
-                      MA_EPI_NONE | MA_LIN_SEG256, st)) return 1;  // split-K by 256 fc1 rows
+                      MA_EPI_NONE, st)) return 1;
     if (launch_layernorm(ws.hres, ws.y16, w->ln2g[L], w->ln2b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
   }
   return 0;
@@ -365,7 +365,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
     const int MEGA_STEPS = 512;
     for (int i = 1; i < max_new && rc == 0; i += MEGA_STEPS) {
       rc = mega_enqueue(w, ws.s, tmax, (__half*)kv, ws.mega, sa, std::min(MEGA_STEPS, max_new - i), i - 1,
-                        ((flags & MA_GEN_TRACE) ? 1 : 0) | ((flags & MA_GEN_WHERE) ? 2 : 0) | ((flags & MA_GEN_TRACE_FINE) ? 5 : 0), st);
+                        (flags & MA_GEN_TRACE) ? 1 : 0, st);
     }
   }
   for (int i = 1; i < max_new && rc == 0 && !mega; i++) {
@@ -443,6 +443,21 @@ int ma_decode_slots_init(int B, int tmax, int pad_id, void* ws_, void* stream) {
       launch_fill_i32(ws.s.tok, pad_id, B, st) || launch_fill_i32(ws.s.finished, 1, B, st) ||
       launch_fill_i32(ws.s.lens, 0, B, st)) return 1;
   return slots_leave(stream, "ma_decode_slots_init");
+}
+
+int ma_decode_slots_seek(int B, int tmax, int pos, int gen, int tok, void* ws_, void* stream) {
+  if (!ws_ || B <= 0 || pos < PREFIX || pos >= tmax || gen < 1) {
+    set_error("ma_decode_slots_seek: bad arguments (pos %d of tmax %d)", pos, tmax);
+    return 1;
+  }
+  std::lock_guard<std::mutex> lock(g_mu);
+  cudaStream_t st;
+  if (slots_enter(stream, &st)) return 1;
+  DecWs ws = carve(ws_, B, tmax, 8195 + 61);
+  if (launch_fill_i32(ws.s.pos, pos, B, st) || launch_fill_i32(ws.s.gen, gen, B, st) ||
+      launch_fill_i32(ws.s.tok, tok, B, st) || launch_fill_i32(ws.s.finished, 0, B, st) ||
+      launch_fill_i32(ws.s.lens, gen, B, st)) return 1;
+  return slots_leave(stream, "ma_decode_slots_seek");
 }
 
 int ma_decode_slot_prefill(const ma_decoder_weights* w, const float* prefix, int slot, int B, int tmax, int max_new,
@@ -532,13 +547,9 @@ int ma_decode_slots_poll(int B, int tmax, void* ws_, int32_t* finished_host, int
 void ma_mega_set_debug(unsigned long long timeout_ns, int fault) { mega_set_debug(timeout_ns, fault); }
 
 int ma_decoder_debug(void* ws_, int B, int tmax, int what, void* host_out, int nbytes) {
-  if (what >= 100) {   // layout query: byte offset of exchange buffer (what - 100) inside the persistent kernel's workspace
-    *(int*)host_out = mega_ws_offset(what - 100);
-    return 0;
-  }
   DecWs ws = carve(ws_, B, tmax, 8195 + 61);
   cudaDeviceSynchronize();
-  const char* src = (const char*)ws.mega + (what == 0 ? mega_error_flag_offset() : what == 1 ? mega_trace_offset() : what == 2 ? mega_trace_cta_offset() : what == 3 ? mega_where_offset() : what == 4 ? mega_fail_offset() : mega_wprog_offset());
+  const char* src = (const char*)ws.mega + (what == 0 ? mega_error_flag_offset() : what == 1 ? mega_trace_offset() : mega_trace_cta_offset());
   return cudaMemcpy(host_out, src, (size_t)nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
 }
 

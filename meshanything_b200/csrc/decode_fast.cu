@@ -177,55 +177,32 @@ __global__ void __launch_bounds__(FG_THREADS) fast_gemv_kernel(FastArgs a) {
     float acc[RB];
 #pragma unroll
     for (int i = 0; i < RB; i++) acc[i] = 0.0f;
-    if constexpr (MODE == MODE_OUT || MODE == MODE_FC2) {
-      // segmented canonical order of the split-K layers: every 256-wide group is reduced on its
-      // own -- out_proj: xor-4,2,1,8,16 (64-element segments first), fc2: the plain butterfly -- and the group values
-      // are added with a balanced tree.  acc[i] ends up holding the finished sum in every lane.
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+#ifdef MA_FHFMA
 #pragma unroll
       for (int i = 0; i < RB; i++) {
         const int r = min(r0 + i, wn - 1);
-        float pg[G];
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          const uint4 u = *reinterpret_cast<const uint4*>(sw + (size_t)(wr0 + r) * K + 256 * g + 8 * lane);
-          pg[g] = dot8(u, xp[g], 0.0f);
-        }
-        float lv[4], tot = 0.0f;
-#pragma unroll
-        for (int g = 0; g < G; g++) {
-          if constexpr (MODE == MODE_OUT) tot = tree4_push(warp_sum_seg64(pg[g]), g, lv);
-          else tot = tree16_push(warp_sum(pg[g]), g, lv);
-        }
-        acc[i] = tot;
+        const uint4 u = *reinterpret_cast<const uint4*>(sw + (size_t)(wr0 + r) * K + 256 * g + 8 * lane);
+        acc[i] = dot8_packed(u, xp[g], acc[i]);
       }
-    } else {
-#pragma unroll
-      for (int g = 0; g < G; g++) {
-#ifdef MA_FHFMA
-#pragma unroll
-        for (int i = 0; i < RB; i++) {
-          const int r = min(r0 + i, wn - 1);
-          const uint4 u = *reinterpret_cast<const uint4*>(sw + (size_t)(wr0 + r) * K + 256 * g + 8 * lane);
-          acc[i] = dot8_packed(u, xp[g], acc[i]);
-        }
 #else
-        float xf[8];
-        unpack8(xp[g], xf);
+      float xf[8];
+      unpack8(xp[g], xf);
 #pragma unroll
-        for (int i = 0; i < RB; i++) {
-          const int r = min(r0 + i, wn - 1);
-          const uint4 u = *reinterpret_cast<const uint4*>(sw + (size_t)(wr0 + r) * K + 256 * g + 8 * lane);
-          float wf[8];
-          unpack8(u, wf);
+      for (int i = 0; i < RB; i++) {
+        const int r = min(r0 + i, wn - 1);
+        const uint4 u = *reinterpret_cast<const uint4*>(sw + (size_t)(wr0 + r) * K + 256 * g + 8 * lane);
+        float wf[8];
+        unpack8(u, wf);
 #pragma unroll
-          for (int j = 0; j < 8; j++) acc[i] = ffma(wf[j], xf[j], acc[i]);
-        }
-#endif
+        for (int j = 0; j < 8; j++) acc[i] = ffma(wf[j], xf[j], acc[i]);
       }
+#endif
     }
 #pragma unroll
     for (int i = 0; i < RB; i++) {
-      const float sum = (MODE == MODE_OUT || MODE == MODE_FC2) ? acc[i] : warp_sum(acc[i]);
+      const float sum = warp_sum(acc[i]);
       const int n = row0 + wr0 + r0 + i;
       if (r0 + i < wn && lane == 0) {
         const float bf = a.bias ? __half2float(a.bias[n]) : 0.0f;

@@ -101,9 +101,5 @@ void mega_set_debug(unsigned long long timeout_ns, int fault);
 int mega_error_flag_offset();
 int mega_trace_offset();
 int mega_trace_cta_offset();
-int mega_where_offset();
-int mega_fail_offset();
-int mega_wprog_offset();
-int mega_ws_offset(int which);
 
 }  // namespace ma

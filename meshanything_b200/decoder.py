@@ -130,11 +130,11 @@ class Generator:
         if lens is not None and bool((lens < 0).any().item()):
             code = self.mega_error()
             raise RuntimeError(f"ma_decode_generate: the persistent decode kernel timed out waiting for another SM "
-                               f"(wait {code & 0xff}, CTA {code >> 8}); no valid token sequence was produced")
+                               f"(first CTA to give up: {code - 1}); no valid token sequence was produced")
 
     def mega_error(self) -> int:
-        """non-zero if a hand-off of the persistent decode kernel timed out (synchronises the device): low byte =
-        which wait, the rest = the CTA that gave up first."""
+        """non-zero if a hand-off of the persistent decode kernel timed out (synchronises the device): 1 + the CTA that
+        gave up first."""
         out = C.c_int(0)
         capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 0, C.byref(out), 4),
                    "ma_decoder_debug")
@@ -147,36 +147,7 @@ class Generator:
                    "ma_decoder_debug")
         return list(buf)
 
-    def mega_fail(self):
-        """post-mortem: the first wait that timed out: dict(code, cta, tid, epoch waited for / seen, buffer, word)."""
-        buf = (C.c_int * 8)()
-        capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 4, buf, 32), "ma_decoder_debug")
-        names = ["qkv_w", "f_w", "pa_w", "pb_w", "ya_w", "yb_w", "cand_w", "part_w", "after"]
-        offs = []
-        for k in range(9):
-            o = C.c_int(0)
-            capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 100 + k, C.byref(o), 4)
-            offs.append(o.value)
-        where, word = "?", -1
-        for k in range(8):
-            if offs[k] <= buf[5] < (offs[k + 1] if k < 7 else offs[8]):
-                where, word = names[k], (buf[5] - offs[k]) // 8
-        return dict(code=buf[0], cta=buf[1], tid=buf[2], ep_wanted=buf[3], ep_seen=buf[4], buffer=where, word=word)
-
-    def mega_wprog(self, n_cta: int = 144):
-        buf = (C.c_int * (n_cta * 16))()
-        capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 5, buf, 4 * n_cta * 16),
-                   "ma_decoder_debug")
-        return [[buf[c * 16 + k] for k in range(16)] for c in range(n_cta)]
-
-    def mega_where(self, n_cta: int = 144):
-        """post-mortem of a time-out: the last phase every CTA reached, as (step, layer, phase, layer instance)."""
-        buf = (C.c_int * (n_cta * 4))()
-        capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 3, buf, 4 * n_cta * 4),
-                   "ma_decoder_debug")
-        return [tuple(buf[c * 4 + k] for k in range(4)) for c in range(n_cta)]
-
-    def mega_trace_cta(self, n_cta: int = 144, n_stamps: int = 16):
+    def mega_trace_cta(self, n_cta: int = 147, n_stamps: int = 8):
         buf = (C.c_uint64 * (n_cta * n_stamps))()
         capi.check(capi.lib().ma_decoder_debug(capi.ptr(self.ws), self.batch, self.tmax, 2, buf, 8 * n_cta * n_stamps),
                    "ma_decoder_debug")

@@ -155,7 +155,9 @@ static inline float tree16(const float *v) {
   return (b[0] + b[1]) + (b[2] + b[3]);
 }
 
-/* Segmented canonical dot (the split-K Linear layers of the decoder): K is cut into 16
+/* Segmented dot -- the order a split-K partition of out_proj / fc2 across SM groups produces.  Round 2 built and
+ * measured that partition (slower than the row split, so the decoder does NOT use it); the
+ * order stays available through orc_linear_seg / MA_LIN_SEG64 / MA_LIN_SEG256 and is unit-tested.  K is cut into 16
  * segments (seg = 64: K = 1024, out_proj -- one segment per attention head; seg = 256: K = 4096, fc2 -- one segment
  * per 256 fc1 rows).  Each segment dot is reduced on its own (lanes run their 8-element fmaf chain from 0; seg 64:
  * xor-4,2,1 butterfly over the segment's 8 lanes; seg 256: the 32-lane butterfly); the 16 segment dots are added
@@ -499,7 +501,7 @@ static void run_tokens(orc_dec *o, float *hid, int M, uint16_t *logits_, int log
         attention_head_canon(q + (size_t)m * HID + hh * HD, kc + (size_t)hh * T * HD, vc + (size_t)hh * T * HD, HD,
                              t0 + m + 1, a + (size_t)m * HID + hh * HD);
     h16_to_xT(a, xT, M, HID);
-    linear_T(l->wo, l->bo, xT, M, HID, HID, 0, 64, y);   /* split-K by head */
+    linear_T(l->wo, l->bo, xT, M, HID, HID, 0, 0, y);
 #pragma omp parallel for schedule(static)
     for (int m = 0; m < M; m++) {
       float h[HID];
@@ -509,7 +511,7 @@ static void run_tokens(orc_dec *o, float *hid, int M, uint16_t *logits_, int log
     to_xT(hid, xT, M, HID);
     linear_T(l->w1, l->b1, xT, M, FFN, HID, 1, 0, f);
     h16_to_xT(f, xT, M, FFN);
-    linear_T(l->w2, l->b2, xT, M, HID, FFN, 0, 256, y);  /* split-K by 256 fc1 rows */
+    linear_T(l->w2, l->b2, xT, M, HID, FFN, 0, 0, y);
 #pragma omp parallel for schedule(static)
     for (int m = 0; m < M; m++) {
       float h[HID];

@@ -51,8 +51,8 @@ def test_greedy_bit_exact_vs_oracle(small, flags):
 
 @gpu
 def test_persistent_kernel_timeout_is_an_error(small):
-    """Fault injection (ma_mega_set_debug): CTA 37 withholds its out_proj partials from the third token on.  The
-    reducers' wait must time out, the kernel must stop emitting tokens, report lens = -1 and an error code, and
+    """Fault injection (ma_mega_set_debug): CTA 37 withholds its out_proj rows from the third token on.  The
+    readers' wait must time out, the kernel must stop emitting tokens, report lens = -1 and an error word, and
     Generator.check() (called by MeshAnything.forward) must raise -- never a silently wrong sequence.  Afterwards the
     same generator works again."""
     import time
@@ -71,8 +71,7 @@ def test_persistent_kernel_timeout_is_an_error(small):
         torch.cuda.synchronize()
         assert time.time() - t0 < 5.0, "a time-out must not take seconds"
         assert int(lens[0]) == -1
-        code = gen.mega_error()
-        assert code != 0 and (code & 0xff) in (4, 5)        # a reducer (4) or a reader of the reduced vector (5) gave up
+        assert gen.mega_error() != 0                        # 1 + the CTA that gave up first
         got = ids[0].cpu().tolist()
         assert got[:3] == good[:3] and all(t == 2 for t in got[3:]), got[:8]   # nothing emitted after the failure
         with pytest.raises(RuntimeError, match="timed out"):
