@@ -6,8 +6,14 @@ of `--faces`*9+2 tokens for `--batch` shapes per GPU (default: BASELINE.json con
 800-face cap, greedy).  Weak scaling: every rank runs the same per-GPU batch on its own shapes;
 the only collective is the weight broadcast at init.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--faces F] [--sampling]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config {2,3,4,5}] [--batch B] [--faces F] [--sampling]
     python bench.py --impl reference ...      # the CPU oracle on the host cores (bounded sample)
+
+--config selects a BASELINE.json configuration (index + 1): 2 = batch 1, 800 faces, greedy (default, the one the metric
+is quoted on); 3 = batch 64, 800 faces, top-k/top-p sampling; 4 = the same per GPU, meant for --gpus 8 (512 shapes);
+5 = batch 32 per GPU, 1600 faces (256 shapes on 8 GPUs), sampling.  The default run also appends an `extra` block:
+bounded decode-step measurements of configs 3 and 5 (200 steps at three context lengths each, KV cache zero-filled and
+the sequence state moved there with ma_decode_slots_seek), each with its own roofline.
 """
 from __future__ import annotations
 
@@ -108,19 +114,84 @@ def cpu_oracle_tokens_per_s(sd, n_layers: int, seconds: float = 12.0):
                       f"OpenMP on {cores} cores"}
 
 
+def batched_decode_steps(arena, n_layers, B, F, sampling, contexts, steps=200, warm=20):
+    """Bounded measurement of the batched decode step (BASELINE configs 3-5) at chosen context lengths: the KV cache is
+    zero-filled, every slot is moved to the context with ma_decode_slots_seek and `steps` steps are timed with CUDA
+    events (device time, CUDA graphs as in ma_decode_generate).  Returns per-context step time, face-tokens/s and the
+    achieved fraction of the HBM roofline (weights once per step + KV of B sequences)."""
+    import ctypes as C
+    from meshanything_b200 import capi
+    from meshanything_b200.config import DEC
+    L = capi.lib()
+    dev = arena.device
+    max_new = DEC.max_new_tokens(F)
+    tmax = 257 + max_new
+    peak, peak_src = measured_peaks()
+    kv_bytes = L.ma_kv_cache_bytes(n_layers, B, tmax)
+    kv = torch.zeros(kv_bytes, dtype=torch.uint8, device=dev)
+    ws = torch.empty(L.ma_decoder_workspace_bytes(B, tmax), dtype=torch.uint8, device=dev)
+    ids = torch.full((B, max_new), 2, dtype=torch.int32, device=dev)
+    samp = capi.Sampling(int(sampling), 50, 0.95, 0)
+    st = capi.stream_ptr()
+    capi.check(L.ma_decode_slots_init(B, tmax, 2, capi.ptr(ws), st), "slots_init")
+    wbytes = arena.weight_bytes_per_step()
+    rows = []
+    for ctx in contexts:
+        ctx = min(ctx, tmax - steps - warm - 4)
+
+        def run(n, c):
+            capi.check(L.ma_decode_slots_step(C.byref(arena.c), B, tmax, max_new, n, c + 1, C.byref(samp), -1, 2,
+                                              capi.ptr(kv), capi.ptr(ws), capi.ptr(ids), 0, st), "slots_step")
+        capi.check(L.ma_decode_slots_seek(B, tmax, ctx, ctx - 256, 5, capi.ptr(ws), st), "slots_seek")
+        run(warm, ctx)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(steps, ctx + warm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        mid = ctx + warm + steps // 2
+        alg = wbytes + B * KV_BYTES_PER_POS * (mid + 1)
+        rows.append({"context": mid, "ms_per_step": ms, "tokens_per_s": B / (ms / 1e3), "algorithmic_bytes": alg,
+                     "achieved_GBps": alg / (ms / 1e3) / 1e9, "frac": alg / (ms / 1e3) / 1e9 / peak})
+    del kv, ws
+    torch.cuda.empty_cache()
+    # harmonic mean over the three contexts ~ a full generate (steps are spread evenly over the contexts)
+    tps = len(rows) / sum(1.0 / r["tokens_per_s"] for r in rows)
+    return {"batch_per_gpu": B, "faces": F, "sampling": bool(sampling), "kv_cache_GB": kv_bytes / 1e9,
+            "steps_timed_per_context": steps, "contexts": rows, "tokens_per_s_over_contexts": tps,
+            "peak_GBps": peak, "peak_source": peak_src,
+            "kernels": "gemm_ws_kernel (tcgen05, swap-AB, split-K) + attention_kernel + sample_kernel in one CUDA graph per step"
+                       if sampling else "gemm_canon_kernel + attention_kernel + sample_kernel in one CUDA graph per step",
+            "note": "decode steps only (no encoder / prefill / detokenizer); KV zero-filled, state set by ma_decode_slots_seek"}
+
+
+CONFIGS = {2: dict(batch=1, faces=800, sampling=False), 3: dict(batch=64, faces=800, sampling=True),
+           4: dict(batch=64, faces=800, sampling=True), 5: dict(batch=32, faces=1600, sampling=True)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="shapes per GPU")
-    ap.add_argument("--faces", type=int, default=800)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs[config-1]")
+    ap.add_argument("--batch", type=int, default=None, help="shapes per GPU (overrides --config)")
+    ap.add_argument("--faces", type=int, default=None)
+    ap.add_argument("--no-extra", action="store_true", help="skip the bounded config-3/5 decode-step block")
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--sampling", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.batch is None:
+        args.batch = cfg["batch"]
+    if args.faces is None:
+        args.faces = cfg["faces"]
+    args.sampling = args.sampling or cfg["sampling"]
 
     from meshanything_b200 import parallel
     from meshanything_b200.checkpoint import decoder_specs, make_state_dict
@@ -131,7 +202,7 @@ def main():
     F, B, NL = args.faces, args.batch, args.layers
     max_new = DEC.max_new_tokens(F)
     face_tokens_per_seq = 9 * F
-    workload = f"350M ({NL} layers), batch={B}/GPU, {F}-face cap ({max_new} new tokens), " + (
+    workload = f"BASELINE configs[{args.config - 1}]: 350M ({NL} layers), batch={B}/GPU, {F}-face cap ({max_new} new tokens), " + (
         "top-k 50 / top-p 0.95 sampling" if args.sampling else "greedy decode")
 
     specs = decoder_specs(NL)
@@ -177,7 +248,8 @@ def main():
     from MeshAnything.models.meshanything import MeshAnything
     full_specs = all_specs(NL)
     sd_host = make_state_dict(full_specs, 0) if rank == 0 else None
-    sd = parallel.broadcast_state_dict(sd_host, full_specs, dev)  # ONE NCCL broadcast; no collective in the step
+    bstats = {}
+    sd = parallel.broadcast_state_dict(sd_host, full_specs, dev, stats=bstats)  # ONE NCCL broadcast; no collective in the step
     del sd_host
     margs = _ap.Namespace(llm="facebook/opt-350m", codebook_size=8192, codebook_dim=1024, n_max_triangles=F, seed=0)
     model = MeshAnything(margs)
@@ -277,7 +349,8 @@ def main():
         "kernel": ("decode_mega_kernel (persistent: all 121 phases of a token, 512 tokens per launch)"
                    if (B == 1 and not args.sampling and not (flags & capi.GEN_NO_MEGA)) else
                    "decode step = 97 fast_gemv_kernel + 24 attention_kernel launches (one CUDA graph)" if B == 1 else
-                   "decode step (gemm_canon + attention kernels, one CUDA graph)"),
+                   "decode step: gemm_ws_kernel (tcgen05 swap-AB split-K) + attention_kernel + sample_kernel, one CUDA graph"
+                   if args.sampling else "decode step (gemm_canon + attention kernels, one CUDA graph)"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": traffic,
         "algorithmic_bytes_per_launch": alg_bytes_per_gen / n_dec,
@@ -289,6 +362,16 @@ def main():
         "prefill_ms": t_prefill_ms,
     }
 
+    extra = None
+    if rank == 0 and world == 1 and args.config == 2 and B == 1 and NL == 24 and not args.no_extra:
+        del gen
+        model._gens.clear()
+        torch.cuda.empty_cache()
+        try:
+            extra = {"config3_batch64_F800_sampling": batched_decode_steps(arena, NL, 64, 800, True, [450, 3850, 7300]),
+                     "config5_batch32_F1600_sampling": batched_decode_steps(arena, NL, 32, 1600, True, [450, 7300, 14400])}
+        except Exception as e:  # noqa: BLE001  (an extra must never cost the headline line)
+            extra = {"error": str(e)[:300]}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -299,6 +382,8 @@ def main():
             "vs_baseline": None, "dtype": "f16 weights/activations, f32 accumulate", "data": "synthetic",
             "config": {"workload": workload, "global_batch": B * world, "parallelism": f"dp{world} (batch sharded, "
                        "weights broadcast once over NCCL)",
+                       "weight_broadcast": {"bytes": bstats.get("bytes"), "ms": bstats.get("ms"),
+                                            "note": "one collective at init, outside the timed region; Linear parameters as fp16"},
                        "inputs": "pc_normal fp16 [B,4096,6] resident in HBM; one step = encoder + generate + detokenize",
                        "stage_ms": {"encoder": ms_enc / args.steps, "generate": ms_gen / args.steps,
                                     "detokenize_and_rest": (ms_all - ms_enc - ms_gen) / args.steps},
@@ -309,7 +394,7 @@ def main():
                     "d2h_bytes_per_step": int(out_e2e.numel() * 4),
                     "api": "MeshAnything.models.meshanything.MeshAnything.forward(pc_normal on the host) -> .cpu()",
                     "first_attempt_ms_discarded": e2e_remeasured},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
             "check": {"first_ids": ids[0, :8].cpu().tolist(), "persistent_kernel_poll_timeouts": int(mega_err)},
         }
         sys.stdout.flush()

@@ -150,6 +150,8 @@ int ma_decode_slots_poll(int B, int tmax, void* ws, int32_t* finished_host, int3
 #define MA_GEN_NO_PDL 4     /* batch-1 fast path without programmatic dependent launch */
 #define MA_GEN_NO_EARLY_EXIT 8
 #define MA_GEN_NO_MEGA 16    /* batch-1 greedy: per-phase kernels (decode_fast.cu) instead of the persistent kernel */
+#define MA_GEN_TC 64         /* batches: decoder GEMMs on the tensor cores (tcgen05) -- logits within a tolerance of the
+                                canonical kernels instead of bit-exact ids; implied by sampling */
 #define MA_GEN_TRACE 32      /* persistent kernel records globaltimer stamps of CTA 0 at every phase boundary */
 
 /* Debug read-back (synchronises the device): what = 0 -> int error word of the persistent kernel (non-zero: a
@@ -166,9 +168,19 @@ void ma_mega_set_debug(unsigned long long timeout_ns, int fault);
  * not bit for bit).  M >= 64, N % 128 == 0, K % 64 == 0.  Used by ma_encoder_forward / ma_detokenize. */
 int ma_linear_tc_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
                      int epilogue, void* stream);
+/* The same contract for FEW rows (1 <= M <= 128; any N; K % 64 == 0): swap-AB weight-streaming tcgen05 GEMM with the K
+ * dimension split across CTAs and a deterministic last-CTA reduction (gemm_ws.cu).  Replaces the cuBLAS GEMMs of HF's
+ * OPTDecoderLayer for a decode step of a batch (shape_opt.py:403-410).  scratch: ma_linear_ws_scratch_bytes() bytes,
+ * zero-filled once by the caller.  Hardware accumulation order: compared under a tolerance. */
+size_t ma_linear_ws_scratch_bytes(void);
+int ma_linear_ws_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
+                     int epilogue, void* scratch, void* stream);
 /* 0: canonical CUDA-core kernels everywhere; 1: encoder / detokenizer GEMMs on the tensor cores; 2: their attention
  * too (ma_attention_tc_f16).  Returns the previous setting. */
 int ma_set_tensor_cores(int enable);
+/* Linear calls of ma_encoder_forward / ma_detokenize since load: how many ran on tcgen05 and how many fell back to the
+ * canonical CUDA-core kernel because their shape cannot be tiled (M < 64, N % 128 != 0). */
+void ma_tensor_core_linear_counts(unsigned long long* on_tcgen05, unsigned long long* canonical_fallback);
 
 /* Dense non-causal attention on the tensor cores (tcgen05 flash attention; replaces F.scaled_dot_product_attention of
  * transformer_blocks.py:57-74,166-185 and BERT's attention in meshanything.py:62-64).  q fp16 [n_slots*rows_per_slot][ldq]
@@ -243,6 +255,15 @@ size_t ma_detokenize_workspace_bytes(int B, int F);
  * faces); ids_out optional int32 [B][9F] = the post-processed ids (-1 = absent). */
 int ma_detokenize(const ma_tokenizer_weights* w, const int32_t* gen_ids, int max_new, int B, int F,
                   const float* point_feature, float* out_xyz, int32_t* ids_out, void* ws, void* stream);
+
+/* ---- mesh -> point cloud ------------------------------------------------------------
+ * Area-weighted surface sampling with face normals: trimesh.Trimesh.sample(count, return_index=True) +
+ * mesh.face_normals[idx] of /root/reference/mesh_to_pc.py:49-53.  vertices fp32 [V][3], faces int32 [F][3] ->
+ * out_pc_normal fp16 [n_samples][6] (point | unit face normal), out_face_idx int32 [n_samples] (optional).  Philox
+ * stream keyed by (seed, sample).  ws: ma_sample_surface_workspace_bytes(F) bytes. */
+size_t ma_sample_surface_workspace_bytes(int n_faces);
+int ma_sample_surface(const float* vertices, const int32_t* faces, int n_faces, int n_samples, unsigned long long seed,
+                      void* out_pc_normal, int32_t* out_face_idx, void* ws, void* stream);
 
 /* number of kernels launched by the library since load (bench.py's gpu_launches) */
 unsigned long long ma_launch_count(void);

@@ -162,13 +162,42 @@ def export_to_watertight(normalized_mesh, octree_depth: int = 7):
     return trimesh.Trimesh(verts, faces, normals=normals)
 
 
+def _gpu_sampler():
+    """The CUDA surface sampler (ma_sample_surface) when a GPU and the library are there; MA_PC_SAMPLER=host keeps the
+    trimesh / numpy sampler (same distribution, numpy's random stream: what the reference draws)."""
+    import os
+    if os.environ.get("MA_PC_SAMPLER", "gpu") != "gpu":
+        return None
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        from meshanything_b200 import capi
+        capi.lib()
+        return capi, torch
+    except Exception:
+        return None
+
+
 def process_mesh_to_pc(mesh_list, marching_cubes=False, sample_num=4096):
-    """[mesh] -> ([fp16 (sample_num, 6) points + face normals], [mesh actually sampled])."""
+    """[mesh] -> ([fp16 (sample_num, 6) points + face normals], [mesh actually sampled]).  On a GPU box the points are
+    drawn by the CUDA sampler (seeded from numpy's generator, so `set_seed` still decides them)."""
     clouds, used = [], []
+    gpu = _gpu_sampler()
     for mesh in mesh_list:
         if marching_cubes:
             mesh = export_to_watertight(mesh)
             print("MC over!")
+        if gpu is not None:
+            capi, torch = gpu
+            dev = torch.device("cuda", torch.cuda.current_device())
+            v = torch.as_tensor(np.asarray(mesh.vertices, dtype=np.float32), device=dev)
+            f = torch.as_tensor(np.asarray(mesh.faces, dtype=np.int32), device=dev)
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+            clouds.append(capi.sample_surface(v, f, sample_num, seed=seed).cpu().numpy())
+            used.append(mesh)
+            print("process mesh success")
+            continue
         pts, tri = mesh.sample(sample_num, return_index=True)
         clouds.append(np.concatenate([pts, mesh.face_normals[tri]], axis=-1, dtype=np.float16))
         used.append(mesh)

@@ -16,7 +16,7 @@ from . import build as _build
 MA_MAX_LAYERS = 32
 EPI_NONE, EPI_RELU, EPI_GELU = 0, 1, 2
 LIN_SEG64, LIN_SEG256 = 0x10, 0x20   # OR-ed into the epilogue: segmented order of the decoder's out_proj / fc2
-GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT, GEN_NO_MEGA, GEN_TRACE = 1, 2, 4, 8, 16, 32
+GEN_NO_GRAPH, GEN_NO_FAST, GEN_NO_PDL, GEN_NO_EARLY_EXIT, GEN_NO_MEGA, GEN_TRACE, GEN_TC = 1, 2, 4, 8, 16, 32, 64
 
 _vp = C.c_void_p
 
@@ -43,7 +43,8 @@ EXPORTS = [
     "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores", "ma_sample_tokens",
     "ma_attention_tc_f16", "ma_transpose_heads_f16",
     "ma_decode_slots_init", "ma_decode_slot_prefill", "ma_decode_slots_step", "ma_decode_slots_poll",
-    "ma_mega_set_debug", "ma_decode_slots_seek",
+    "ma_mega_set_debug", "ma_decode_slots_seek", "ma_linear_ws_scratch_bytes", "ma_linear_ws_f16",
+    "ma_sample_surface_workspace_bytes", "ma_sample_surface", "ma_tensor_core_linear_counts",
 ]
 
 
@@ -100,8 +101,15 @@ def lib():
     L.ma_detokenize_workspace_bytes.argtypes = [C.c_int, C.c_int]
     L.ma_detokenize_workspace_bytes.restype = C.c_size_t
     L.ma_detokenize.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]
+    L.ma_linear_ws_scratch_bytes.restype = C.c_size_t
+    L.ma_linear_ws_f16.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.ma_sample_surface_workspace_bytes.argtypes = [C.c_int]
+    L.ma_sample_surface_workspace_bytes.restype = C.c_size_t
+    L.ma_sample_surface.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_ulonglong, _vp, _vp, _vp, _vp]
     L.ma_linear_tc_f16.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]
     L.ma_set_tensor_cores.argtypes = [C.c_int]
+    L.ma_tensor_core_linear_counts.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    L.ma_tensor_core_linear_counts.restype = None
     if L.ma_abi_version() != 1:
         raise RuntimeError("libmeshanything_b200.so: ABI version mismatch")
     _lib = L
@@ -141,6 +149,45 @@ def linear_f16(w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor, e
         out = torch.empty((M, N), dtype=torch.float16, device=x.device)
     check(lib().ma_linear_f16(ptr(w), ptr(bias), ptr(x), x.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
                               stream_ptr()), "ma_linear_f16")
+    return out
+
+
+def sample_surface(vertices: torch.Tensor, faces: torch.Tensor, n_samples: int, seed: int = 0,
+                   want_index: bool = False):
+    """Area-weighted surface samples + face normals on the GPU: fp16 [n_samples, 6] (and the face of every sample)."""
+    _need_cuda(vertices, faces)
+    v = vertices.to(torch.float32).contiguous()
+    f = faces.to(torch.int32).contiguous()
+    F = f.shape[0]
+    ws = torch.empty(lib().ma_sample_surface_workspace_bytes(F), dtype=torch.uint8, device=v.device)
+    out = torch.empty((n_samples, 6), dtype=torch.float16, device=v.device)
+    idx = torch.empty((n_samples,), dtype=torch.int32, device=v.device) if want_index else None
+    check(lib().ma_sample_surface(ptr(v), ptr(f), F, n_samples, int(seed), ptr(out), ptr(idx), ptr(ws), stream_ptr()),
+          "ma_sample_surface")
+    return (out, idx) if want_index else out
+
+
+def tensor_core_linear_counts():
+    """(Linear calls of the encoder / detokenizer that ran on tcgen05, calls that fell back to the canonical kernel)."""
+    a, b = C.c_ulonglong(0), C.c_ulonglong(0)
+    lib().ma_tensor_core_linear_counts(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+_ws_scratch = {}
+
+
+def linear_ws_f16(w: torch.Tensor, bias: Optional[torch.Tensor], x: torch.Tensor, epilogue: int = EPI_NONE) -> torch.Tensor:
+    """fp16(x @ w.T + bias) for M <= 128 rows on the weight-streaming tcgen05 GEMM (hardware accumulation order)."""
+    _need_cuda(w, bias, x)
+    M, K = x.shape
+    N = w.shape[0]
+    scr = _ws_scratch.get(x.device)
+    if scr is None:
+        scr = _ws_scratch[x.device] = torch.zeros(lib().ma_linear_ws_scratch_bytes(), dtype=torch.uint8, device=x.device)
+    out = torch.empty((M, N), dtype=torch.float16, device=x.device)
+    check(lib().ma_linear_ws_f16(ptr(w), ptr(bias), ptr(x), x.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
+                                 ptr(scr), stream_ptr()), "ma_linear_ws_f16")
     return out
 
 

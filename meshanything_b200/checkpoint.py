@@ -181,3 +181,15 @@ def synthetic_decoder_state_dict(seed: int = 0, n_layers: int = DEC.n_layers) ->
 
 def synthetic_state_dict(seed: int = 0, n_dec_layers: int = DEC.n_layers) -> Dict[str, torch.Tensor]:
     return make_state_dict(all_specs(n_dec_layers), seed)
+
+
+_FP32_PATTERNS = ("LayerNorm.", "ln_1.", "ln_2.", "ln_3.", "ln_post.", "layernorm.", "layer_norm.", "norm1_", "norm2_", "embed_positions",
+                  "extra_embeds", "token_embed_positions", "cond_embed", "pos_embedding", "point_pe", ".query",
+                  "quantize_codebooks", "shape_projection", "geo_decoder")
+
+
+def consumed_as_fp16(name: str) -> bool:
+    """True for the parameters the arenas keep as fp16 (`nn.Linear` weights and biases: exactly the values autocast
+    would produce with `tensor.half()`); LayerNorm affine parameters, embedding tables, the Perceiver query and the VQ
+    codebook stay fp32.  Used by parallel.broadcast_state_dict to ship fp16 where fp16 is what is kept."""
+    return not any(p in name for p in _FP32_PATTERNS)

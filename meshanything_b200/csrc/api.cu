@@ -51,6 +51,7 @@ struct DecWs {
   size_t attn_scratch_pre_bytes;  // partials) depends on M and a slot prefill may follow decode steps
   void* fast;
   void* mega;
+  void* tc_scratch;   // gemm_ws.cu: fp32 K-slice partials + tickets
   size_t total;
 };
 
@@ -84,6 +85,7 @@ static DecWs carve(void* base, int B, int tmax, int vocab) {
   w.attn_scratch_pre = take(w.attn_scratch_pre_bytes);
   w.fast = take(fast_workspace_bytes());
   w.mega = take(mega_workspace_bytes());
+  w.tc_scratch = take(linear_ws_scratch_bytes());
   w.total = off;
   return w;
 }
@@ -93,24 +95,33 @@ static inline __half* kv_layer(void* kv, int layer, int which, int B, long T) {
 }
 
 // One pass of the 24 layers over M rows (general batched kernels).
+// y = act(x W^T + b) for M rows of the decoder: the canonical kernel, or (tc) the tensor cores -- the weight-streaming
+// tcgen05 GEMM for M <= 128 rows (decode steps), the tiled tcgen05 GEMM for the 257-row prefill passes
+static int dec_linear(bool tc, const DecWs& ws, const void* W, const void* b, const __half* x, int ldx, __half* y, int ldy,
+                      int M, int N, int K, int epi, cudaStream_t st) {
+  if (tc) {
+    if (M <= 128 && linear_ws_supported(M, N, K, ldx, x, W))
+      return launch_linear_ws((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, ws.tc_scratch, st);
+    if (M > 128 && linear_tc_supported(M, N, K, ldx, ldy, x, W, y))
+      return launch_linear_tc((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
+  }
+  return launch_linear((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
+}
+
 static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, int B, long T, int M, int rows_per_slot,
-                      int slot0, int max_keys, cudaStream_t st) {
+                      int slot0, int max_keys, cudaStream_t st, bool tc = false) {
   void* scratch = rows_per_slot > 1 ? ws.attn_scratch_pre : ws.attn_scratch;
   for (int L = 0; L < w->n_layers; L++) {
     __half* kc = kv_layer(kv, L, 0, B, T) + (size_t)slot0 * NHEAD * T * HD;
     __half* vc = kv_layer(kv, L, 1, B, T) + (size_t)slot0 * NHEAD * T * HD;
-    if (launch_linear((const __half*)w->wqkv[L], (const __half*)w->bqkv[L], ws.x16, HID, ws.qkv, QKV, M, QKV, HID,
-                      MA_EPI_NONE, st)) return 1;
+    if (dec_linear(tc, ws, w->wqkv[L], w->bqkv[L], ws.x16, HID, ws.qkv, QKV, M, QKV, HID, MA_EPI_NONE, st)) return 1;
     if (launch_kv_append(ws.qkv, M, rows_per_slot, ws.nkeys, kc, vc, T, st)) return 1;
     if (launch_attention(ws.qkv, QKV, kc, vc, T, NHEAD, rows_per_slot, nullptr, ws.nkeys, max_keys, M, 0.125f,
                          ws.attn16, HID, scratch, st)) return 1;
-    if (launch_linear((const __half*)w->wo[L], (const __half*)w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID,
-                      MA_EPI_NONE, st)) return 1;
+    if (dec_linear(tc, ws, w->wo[L], w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID, MA_EPI_NONE, st)) return 1;
     if (launch_layernorm(ws.hres, ws.y16, w->ln1g[L], w->ln1b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
-    if (launch_linear((const __half*)w->w1[L], (const __half*)w->b1[L], ws.x16, HID, ws.f16, FFN, M, FFN, HID,
-                      MA_EPI_RELU, st)) return 1;
-    if (launch_linear((const __half*)w->w2[L], (const __half*)w->b2[L], ws.f16, FFN, ws.y16, HID, M, HID, FFN,
-                      MA_EPI_NONE, st)) return 1;
+    if (dec_linear(tc, ws, w->w1[L], w->b1[L], ws.x16, HID, ws.f16, FFN, M, FFN, HID, MA_EPI_RELU, st)) return 1;
+    if (dec_linear(tc, ws, w->w2[L], w->b2[L], ws.f16, FFN, ws.y16, HID, M, HID, FFN, MA_EPI_NONE, st)) return 1;
     if (launch_layernorm(ws.hres, ws.y16, w->ln2g[L], w->ln2b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
   }
   return 0;
@@ -162,13 +173,16 @@ static int ensure_globals() {
 
 // One decode step of the whole batch on the general kernels (embed -> 24 layers -> lm_head -> pick).
 static int enqueue_batched_step(const ma_decoder_weights* w, const DecWs& ws, void* kv, int B, long T, int max_keys,
-                                const SampleArgs& sa, cudaStream_t s) {
+                                const SampleArgs& sa, cudaStream_t s, bool tc) {
   if (launch_embed_tokens(w, ws.s, B, ws.hres, ws.x16, ws.nkeys, s)) return 1;
-  if (run_layers(w, ws, kv, B, T, B, 1, 0, max_keys, s)) return 1;
-  if (launch_linear((const __half*)w->lm_head, nullptr, ws.x16, HID, ws.logits, w->vocab, B, w->vocab, HID,
-                    MA_EPI_NONE, s)) return 1;
+  if (run_layers(w, ws, kv, B, T, B, 1, 0, max_keys, s, tc)) return 1;
+  if (dec_linear(tc, ws, w->lm_head, nullptr, ws.x16, HID, ws.logits, w->vocab, B, w->vocab, HID, MA_EPI_NONE, s)) return 1;
   return launch_sample(sa, s);
 }
+
+// Tensor-core GEMMs in the decoder: batches only (one sequence is a GEMV, HBM-bound on the canonical kernels), and only
+// where ids are not promised bit for bit: sampling (logits tolerance, BASELINE configs 3-5) or MA_GEN_TC
+static inline bool use_tc(int B, int do_sample, int flags) { return B > 1 && (do_sample || (flags & MA_GEN_TC)); }
 
 static unsigned long long weights_hash(const ma_decoder_weights* w) {
   unsigned long long h = 1469598103934665603ull;  // FNV-1a over the pointer table: graphs bake the pointers in
@@ -264,6 +278,14 @@ int ma_linear_f16(const void* W, const void* bias, const void* x, int ldx, void*
                        epilogue, (cudaStream_t)stream);
 }
 
+size_t ma_linear_ws_scratch_bytes(void) { return linear_ws_scratch_bytes(); }
+
+int ma_linear_ws_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
+                     int epilogue, void* scratch, void* stream) {
+  return launch_linear_ws((const __half*)W, (const __half*)bias, (const __half*)x, ldx, (__half*)y, ldy, M, N, K,
+                          epilogue, scratch, (cudaStream_t)stream);
+}
+
 int ma_layernorm(const float* x, const void* res16, const float* gamma, const float* beta, float eps, int M, int W,
                  float* out32, void* out16, void* stream) {
   return launch_layernorm(x, (const __half*)res16, gamma, beta, eps, M, W, out32, (__half*)out16,
@@ -333,6 +355,8 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   sa.first = 1; sa.forced = forced_ids; sa.logits_out = (__half*)logits_out;
   sa.all_done = ws.all_done;
 
+  const bool tc = use_tc(B, sa.do_sample, flags);
+  if (tc) cudaMemsetAsync(ws.tc_scratch, 0, linear_ws_scratch_bytes(), st);   // tickets start at zero
   const bool fast = (B == 1) && !(flags & MA_GEN_NO_FAST);
   // the persistent kernel needs 144 co-resident CTAs and tmax <= 15360 keys; otherwise the per-phase kernels run
   bool mega = fast && !sa.do_sample && !(flags & MA_GEN_NO_MEGA) && mega_fits(tmax) && mega_supported();
@@ -343,11 +367,11 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
   for (int b0 = 0; b0 < B; b0 += PREFILL_SEQS) {
     const int nb = std::min(PREFILL_SEQS, B - b0), M = nb * PREFIX;
     if (launch_embed_prefix(w, prefix + (size_t)b0 * PREFIX * HID, nb, ws.hres, ws.x16, ws.nkeys, st)) return 1;
-    if (run_layers(w, ws, kv, B, T, M, PREFIX, b0, PREFIX, st)) return 1;
+    if (run_layers(w, ws, kv, B, T, M, PREFIX, b0, PREFIX, st, tc)) return 1;
     if (launch_gather_rows(ws.x16, HID, PREFIX - 1, PREFIX, nb, ws.lastx16 + (size_t)b0 * HID, st)) return 1;
   }
-  if (launch_linear((const __half*)w->lm_head, nullptr, ws.lastx16, HID, ws.logits, w->vocab, B, w->vocab, HID,
-                    MA_EPI_NONE, st)) return 1;
+  if (dec_linear(tc, ws, w->lm_head, nullptr, ws.lastx16, HID, ws.logits, w->vocab, B, w->vocab, HID, MA_EPI_NONE, st))
+    return 1;
   if (launch_sample(sa, st)) return 1;
   sa.first = 0;
   sa.nkeys_next = nullptr;
@@ -374,7 +398,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
     const int max_keys = fast ? tmax : std::min(tmax, bucket * 1024);
     auto enqueue = [&](cudaStream_t s) -> int {
       if (fast) return fast_step_enqueue(w, ws.s, tmax, (__half*)kv, ws.fast, sa, !(flags & MA_GEN_NO_PDL), s);
-      return enqueue_batched_step(w, ws, kv, B, T, max_keys, sa, s);
+      return enqueue_batched_step(w, ws, kv, B, T, max_keys, sa, s, tc);
     };
     if (!use_graph) {
       rc = enqueue(st);
@@ -438,6 +462,7 @@ int ma_decode_slots_init(int B, int tmax, int pad_id, void* ws_, void* stream) {
   DecWs ws = carve(ws_, B, tmax, 8195 + 61);
   cudaMemsetAsync(ws.attn_scratch, 0, ws.attn_scratch_bytes, st);
   cudaMemsetAsync(ws.attn_scratch_pre, 0, ws.attn_scratch_pre_bytes, st);
+  cudaMemsetAsync(ws.tc_scratch, 0, linear_ws_scratch_bytes(), st);
   // every slot starts free: finished, nothing generated, a valid (pad) token at a valid position
   if (launch_fill_i32(ws.s.pos, PREFIX, B, st) || launch_fill_i32(ws.s.gen, 0, B, st) ||
       launch_fill_i32(ws.s.tok, pad_id, B, st) || launch_fill_i32(ws.s.finished, 1, B, st) ||
@@ -475,11 +500,12 @@ int ma_decode_slot_prefill(const ma_decoder_weights* w, const float* prefix, int
   DecWs ws = carve(ws_, B, tmax, 8195 + 61);
   if (launch_fill_i32(out_ids + (size_t)slot * max_new, pad_id, max_new, st)) return 1;
   if (launch_embed_prefix(w, prefix, 1, ws.hres, ws.x16, ws.nkeys, st)) return 1;
-  if (run_layers(w, ws, kv, B, T, PREFIX, PREFIX, slot, PREFIX, st)) return 1;
+  const bool tc = use_tc(B, sampling ? sampling->do_sample : 0, 0);
+  if (run_layers(w, ws, kv, B, T, PREFIX, PREFIX, slot, PREFIX, st, tc)) return 1;
   __half* last = ws.lastx16 + (size_t)slot * HID;
   if (launch_gather_rows(ws.x16, HID, PREFIX - 1, PREFIX, 1, last, st)) return 1;
-  if (launch_linear((const __half*)w->lm_head, nullptr, last, HID, ws.logits + (size_t)slot * w->vocab, w->vocab, 1,
-                    w->vocab, HID, MA_EPI_NONE, st)) return 1;
+  if (dec_linear(tc, ws, w->lm_head, nullptr, last, HID, ws.logits + (size_t)slot * w->vocab, w->vocab, 1, w->vocab, HID,
+                 MA_EPI_NONE, st)) return 1;
   SampleArgs sa;
   fill_sample_args(sa, w, ws, B, max_new, sampling, eos_id, pad_id, out_ids);
   sa.first = 1; sa.row0 = slot; sa.nrows = 1; sa.slots = 1;
@@ -509,7 +535,9 @@ int ma_decode_slots_step(const ma_decoder_weights* w, int B, int tmax, int max_n
     const int ctx = std::min(tmax, max_ctx + i);   // upper bound of the keys any live slot sees at this step
     const int bucket = (ctx + 1023) / 1024;
     const int max_keys = std::min(tmax, bucket * 1024);
-    auto enqueue = [&](cudaStream_t s) -> int { return enqueue_batched_step(w, ws, kv, B, T, max_keys, sa, s); };
+    auto enqueue = [&](cudaStream_t s) -> int {
+      return enqueue_batched_step(w, ws, kv, B, T, max_keys, sa, s, use_tc(B, sa.do_sample, flags));
+    };
     if (!use_graph) {
       if (enqueue(st)) return 1;
     } else {

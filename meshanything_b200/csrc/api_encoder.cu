@@ -73,9 +73,14 @@ static int g_use_tc = 2;  // 0: canonical CUDA-core kernels; 1: GEMMs of the enc
                           // 2: their attention on tcgen05 too (ma_set_tensor_cores)
 
 // nn.Linear of the tolerance-checked stages: tensor cores when the shape allows, canonical CUDA-core kernel otherwise
+static unsigned long long g_tc_calls = 0, g_tc_fallbacks = 0;   // Linear calls of these stages: on tcgen05 / not tileable
 static int enc_linear(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
                       int K, int epi, cudaStream_t st) {
-  if (g_use_tc && linear_tc_supported(M, N, K, ldx, ldy, x, W, y)) return launch_linear_tc(W, bias, x, ldx, y, ldy, M, N, K, epi, st);
+  if (g_use_tc && linear_tc_supported(M, N, K, ldx, ldy, x, W, y)) {
+    g_tc_calls++;
+    return launch_linear_tc(W, bias, x, ldx, y, ldy, M, N, K, epi, st);
+  }
+  if (g_use_tc) g_tc_fallbacks++;   // small-M / odd shapes (cond_head_proj on 1 row per shape, pre_kl N = 128 ...)
   return launch_linear(W, bias, x, ldx, y, ldy, M, N, K, epi, st);
 }
 
@@ -271,6 +276,11 @@ static int detok_chunk(const ma_tokenizer_weights* t, const int32_t* gen_ids, in
 using namespace ma;
 
 extern "C" {
+
+void ma_tensor_core_linear_counts(unsigned long long* on_tcgen05, unsigned long long* canonical_fallback) {
+  if (on_tcgen05) *on_tcgen05 = g_tc_calls;
+  if (canonical_fallback) *canonical_fallback = g_tc_fallbacks;
+}
 
 int ma_set_tensor_cores(int enable) {
   const int old = g_use_tc;

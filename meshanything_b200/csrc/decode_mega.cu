@@ -175,7 +175,7 @@ struct alignas(128) MegaSmem {
   alignas(16) __half bias[2][128];
   ma_decoder_weights wtab;          // pointer table (kept on chip: every access would be an HBM miss)
   int errflag;
-  float red[8];
+  float red[2][8];   // LayerNorm: warp sums of the mean pass / of the variance pass
   float wmax[2][8];
   float ared[2][8][65];
   float bval[MG_WARPS];
@@ -192,32 +192,29 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // LayerNorm of 1024 values by the first 256 threads (thread t owns 4t..4t+3: the canonical block sum); the other
 // threads only take part in the barriers.  Returns the normalised values in v (threads < 256).
-__device__ __forceinline__ void layernorm_1024(float* v, const float* gamma, const float* beta, float* red, int tid) {
+// Only warps 0-7 take part (named barrier 3); the other warps go straight to the caller's __syncthreads.
+__device__ __forceinline__ void layernorm_1024(float* v, const float* gamma, const float* beta, float (*red)[8], int tid) {
+  if (tid >= 256) return;
   const int warp = tid >> 5, lane = tid & 31;
-  const bool act = tid < 256;
   const float inv = __fdiv_rn(1.0f, 1024.0f);
-  float p = act ? fadd(fadd(v[0], v[1]), fadd(v[2], v[3])) : 0.0f;
+  float p = fadd(fadd(v[0], v[1]), fadd(v[2], v[3]));
   p = warp_sum(p);
-  __syncthreads();
-  if (act && lane == 0) red[warp] = p;
-  __syncthreads();
-  const float mean = fmul(warp_tree(red, 8), inv);
+  if (lane == 0) red[0][warp] = p;
+  asm volatile("bar.sync 3, 256;" ::: "memory");
+  const float mean = fmul(warp_tree(red[0], 8), inv);
   const float d0 = fsub(v[0], mean), d1 = fsub(v[1], mean), d2 = fsub(v[2], mean), d3 = fsub(v[3], mean);
-  float q = act ? fadd(fadd(fmul(d0, d0), fmul(d1, d1)), fadd(fmul(d2, d2), fmul(d3, d3))) : 0.0f;
+  float q = fadd(fadd(fmul(d0, d0), fmul(d1, d1)), fadd(fmul(d2, d2), fmul(d3, d3)));
   q = warp_sum(q);
-  __syncthreads();
-  if (act && lane == 0) red[warp] = q;
-  __syncthreads();
-  const float var = fmul(warp_tree(red, 8), inv);
+  if (lane == 0) red[1][warp] = q;
+  asm volatile("bar.sync 3, 256;" ::: "memory");
+  const float var = fmul(warp_tree(red[1], 8), inv);
   const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(fadd(var, MA_LN_EPS)));
-  if (act) {
-    const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * tid);
-    const float4 b = *reinterpret_cast<const float4*>(beta + 4 * tid);
-    v[0] = ffma(fmul(d0, rstd), g.x, b.x);
-    v[1] = ffma(fmul(d1, rstd), g.y, b.y);
-    v[2] = ffma(fmul(d2, rstd), g.z, b.z);
-    v[3] = ffma(fmul(d3, rstd), g.w, b.w);
-  }
+  const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * tid);
+  const float4 b = *reinterpret_cast<const float4*>(beta + 4 * tid);
+  v[0] = ffma(fmul(d0, rstd), g.x, b.x);
+  v[1] = ffma(fmul(d1, rstd), g.y, b.y);
+  v[2] = ffma(fmul(d2, rstd), g.z, b.z);
+  v[3] = ffma(fmul(d3, rstd), g.w, b.w);
 }
 
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(TEAM) : "memory"); }
@@ -500,12 +497,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
           mbar_wait(&sm.lnbar[1], parL2);
           parL2 ^= 1;
           layernorm_1024(v, sm.ln2, sm.ln2 + HID, sm.red, tid);
-          __syncthreads();  // every thread has read its gamma/beta
-          if (tid == 0) fill_ln(sm.ln2, W.ln2g[L], W.ln2b[L], &sm.lnbar[1]);
         }
         publish_x(v, true);
       }
-      __syncthreads();
+      __syncthreads();   // xs complete; every thread has read its gamma/beta
+      if (L > 0 && tid == 0) fill_ln(sm.ln2, W.ln2g[L], W.ln2b[L], &sm.lnbar[1]);
       STAMP();
       CSTAMP(0);
       mbar_wait(&sm.bbar[bsel], bsel ? parB1 : parB0);
@@ -787,11 +783,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
         mbar_wait(&sm.lnbar[0], parL1);
         parL1 ^= 1;
         layernorm_1024(v, sm.ln1, sm.ln1 + HID, sm.red, tid);
-        __syncthreads();
-        if (tid == 0) fill_ln(sm.ln1, W.ln1g[(L + 1) % NL], W.ln1b[(L + 1) % NL], &sm.lnbar[0]);
         publish_x(v, true);
       }
       __syncthreads();
+      if (tid == 0) fill_ln(sm.ln1, W.ln1g[(L + 1) % NL], W.ln1b[(L + 1) % NL], &sm.lnbar[0]);
       mbar_wait(&sm.bar[2], parA);
       parA ^= 1;
       gemv_stage<HID, true>(bufA, n_fc1, lb + BIAS_FC1, sm.xs, warp, lane, sm.stage16);
@@ -837,11 +832,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(MegaArgs a) 
       mbar_wait(&sm.lnbar[1], parL2);
       parL2 ^= 1;
       layernorm_1024(v, sm.ln2, sm.ln2 + HID, sm.red, tid);
-      __syncthreads();
-      if (tid == 0) fill_ln(sm.ln2, W.ln2g[0], W.ln2b[0], &sm.lnbar[1]);
       publish_x(v, false);
     }
     __syncthreads();
+    if (tid == 0) fill_ln(sm.ln2, W.ln2g[0], W.ln2b[0], &sm.lnbar[1]);
     mbar_wait(&sm.bar[0], parD);
     mbar_wait(&sm.bar[1], parC);
     mbar_wait(&sm.bar[2], parA);

@@ -45,6 +45,12 @@ bool linear_tc_supported(int M, int N, int K, int ldx, int ldy, const void* x, c
 int launch_linear_tc(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
                      int K, int epi, cudaStream_t st);
 
+// gemm_ws.cu (tcgen05 weight-streaming GEMM for M <= 128 rows: batched decode steps under a tolerance)
+size_t linear_ws_scratch_bytes();
+bool linear_ws_supported(int M, int N, int K, int ldx, const void* x, const void* W);
+int launch_linear_ws(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
+                     int K, int epi, void* scratch, cudaStream_t st);
+
 // attention.cu
 size_t attention_scratch_bytes(int M, int H, int max_keys);
 int launch_attention(const __half* q, int ldq, const __half* K, const __half* V, long T, int H, int rows_per_slot,

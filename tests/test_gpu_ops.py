@@ -135,6 +135,38 @@ def test_linear_tensor_core(M, N, K, epi):
     assert (diff == 0).float().mean() > 0.98
 
 
+@gpu
+@pytest.mark.parametrize("M,N,K,epi", [(1, 1024, 1024, 0), (5, 3072, 1024, 0), (16, 1024, 4096, 0), (33, 4096, 1024, 1),
+                                        (64, 1024, 1024, 0), (64, 8195, 1024, 0), (128, 4096, 1024, 1), (100, 768, 3072, 2),
+                                        (2, 200, 64, 0)])
+def test_linear_weight_streaming_tensor_core(M, N, K, epi):
+    """gemm_ws_kernel (swap-AB tcgen05 GEMM for M <= 128 rows, K split across CTAs, deterministic last-CTA reduction):
+    fp16 in, fp32 accumulate in the hardware's order -> compared with an fp64 product rounded once to fp16 and with the
+    canonical kernel; two runs give identical bits (the K-slice sum does not depend on which CTA finishes last)."""
+    from meshanything_b200 import capi
+    g = torch.Generator().manual_seed(M * 31 + N + K)
+    w = (torch.randn(N, K, generator=g) * 0.05).half()
+    b = (torch.randn(N, generator=g) * 0.1).half() if N != 8195 else None       # lm_head has no bias
+    x = torch.randn(M, K, generator=g).half()
+    d = _dev()
+    wd, bd, xd = w.to(d), (b.to(d) if b is not None else None), x.to(d)
+    got = capi.linear_ws_f16(wd, bd, xd, epilogue=epi).cpu()
+    again = capi.linear_ws_f16(wd, bd, xd, epilogue=epi).cpu()
+    assert torch.equal(got.view(torch.int16), again.view(torch.int16))
+    pre = x.double() @ w.double().T + (b.double() if b is not None else 0.0)
+    if epi == 1:
+        pre = torch.relu(pre)
+    elif epi == 2:
+        pre = torch.nn.functional.gelu(pre.half().double())
+    tol = 2.0 ** -10 * pre.abs() + 2e-3
+    assert ((got.double() - pre).abs() <= tol).all(), (got.double() - pre).abs().max()
+    if K % 256 == 0:
+        canon = capi.linear_f16(wd, bd, xd, epilogue=epi).cpu()
+        diff = (got.float() - canon.float()).abs()
+        assert (diff <= 2.0 ** -9 * canon.float().abs() + 1e-3).all()
+        assert (diff == 0).float().mean() > 0.97
+
+
 def _hf_support(row: torch.Tensor, top_k: int, top_p: float):
     """Support after transformers' own TopKLogitsWarper -> TopPLogitsWarper (the chain HF _sample builds for
     meshanything.py:150-158), evaluated in fp32 on the CPU.  Returns (ids by descending logit, near_boundary)."""

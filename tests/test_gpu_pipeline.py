@@ -247,3 +247,138 @@ def test_kernel_selections_all_meet_the_tolerance(full):
     finally:
         capi.lib().ma_set_tensor_cores(old)
     assert (outs[0] - outs[2]).abs().max() < 2 * TOL_PF_MAX and (outs[1] - outs[2]).abs().max() < 2 * TOL_PF_MAX
+
+
+@gpu
+def test_gpu_surface_sampler_matches_the_numpy_sampler_distribution():
+    """ma_sample_surface (area-weighted face pick by inverse CDF, uniform barycentric point, face normal)
+    against the numpy restatement of trimesh's sampler in mesh_to_pc.SimpleMesh: the per-face hit counts of 200 000
+    samples follow the face areas (the numpy sampler's own counts are checked with the same bound), every point lies in
+    its face's plane inside the triangle, the normal is the face normal, and process_mesh_to_pc uses it on a GPU box."""
+    import numpy as np
+    import mesh_to_pc
+    from meshanything_b200 import capi
+    rng = np.random.RandomState(3)
+    V, F, n = 300, 500, 200_000
+    verts = rng.randn(V, 3).astype(np.float32)
+    faces = np.stack([rng.choice(V, 3, replace=False) for _ in range(F)]).astype(np.int32)
+    # a few degenerate and tiny faces: they must (almost) never be hit
+    faces[7] = [5, 5, 9]
+    verts[faces[11, 1]] = verts[faces[11, 0]] + 1e-4
+    mesh = mesh_to_pc.SimpleMesh(verts, faces)
+    tri = verts[faces].astype(np.float64)
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    p = area / area.sum()
+    out, idx = capi.sample_surface(torch.from_numpy(verts).to(_dev()), torch.from_numpy(faces).to(_dev()), n, seed=5,
+                                   want_index=True)
+    out, idx = out.cpu().float().numpy(), idx.cpu().numpy()
+    counts = np.bincount(idx, minlength=F)
+    sigma = np.sqrt(n * p * (1 - p)) + 1.0
+    assert (np.abs(counts - n * p) < 5 * sigma).all()
+    assert counts[7] == 0
+    np.random.seed(0)
+    _, idx_np = mesh.sample(n, return_index=True)
+    assert (np.abs(np.bincount(idx_np, minlength=F) - n * p) < 5 * sigma).all()      # same law for the host sampler
+    # geometry: barycentric coordinates of every point w.r.t. its face are in [0, 1] (fp16 rounding of the output)
+    a, b, c = tri[idx, 0], tri[idx, 1], tri[idx, 2]
+    nrm = np.cross(b - a, c - a)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    pts = out[:, :3].astype(np.float64)
+    scale = np.abs(tri).max()
+    assert np.abs(((pts - a) * nrm).sum(1)).max() < 4e-3 * scale                     # in the plane
+    m = np.stack([b - a, c - a], axis=2)                                             # [n, 3, 2]
+    sol = np.einsum("nij,nj->ni", np.linalg.pinv(m), pts - a)
+    assert sol.min() > -2e-2 and (sol.sum(1)).max() < 1 + 2e-2
+    assert np.abs(out[:, 3:] - nrm).max() < 2e-3
+    # uniform inside a triangle: the mean barycentric coordinates of the samples of the largest face are 1/3
+    big = int(np.argmax(area))
+    sb = sol[idx == big]
+    assert len(sb) > 1000 and np.abs(sb.mean(0) - 1.0 / 3.0).max() < 0.03
+    # the drop-in entry point uses the GPU sampler here and returns what the reference returns
+    np.random.seed(1)
+    clouds, used = mesh_to_pc.process_mesh_to_pc([mesh])
+    assert clouds[0].shape == (4096, 6) and clouds[0].dtype == np.float16 and used[0] is mesh
+    assert np.abs(np.linalg.norm(clouds[0][:, 3:].astype(np.float32), axis=1) - 1).max() < 2e-3
+
+
+@gpu
+def test_safetensors_checkpoint_round_trip(tmp_path):
+    """SURVEY 8(f)4 / main.py:95-104: a safetensors file with the published key list (fp32 tensors, BERT layers in the
+    optimum-BetterTransformer spelling) goes through `main.load_model` into the fp16 / fp32 arenas and gives exactly the
+    mesh of a model loaded from the in-memory tensors; the same checkpoint re-saved with plain HF BertLayer names
+    (what `BetterTransformer.reverse` or a non-optimum save would produce) loads to the same result; a missing or an
+    unexpected key is an error under strict=True, as in the reference."""
+    import main as cli
+    from safetensors.torch import save_file
+    from MeshAnything.models.meshanything import MeshAnything
+    NL = 2                                                    # decoder layers (keeps the file at ~1.3 GB)
+    specs = ck.all_specs(NL)
+    sd = ck.make_state_dict(specs, 0)
+    args = argparse.Namespace(llm="facebook/opt-350m", codebook_size=8192, codebook_dim=1024, n_max_triangles=6, seed=0,
+                              pretrained_weights=str(tmp_path / "MeshAnything_350m.pth"))
+    save_file({k: v.contiguous() for k, v in sd.items()}, args.pretrained_weights)
+    orig_expected = MeshAnything.expected_keys
+    MeshAnything.expected_keys = lambda self: list(specs.keys())
+    try:
+        model = cli.load_model(args, device=_dev())
+        ref = MeshAnything(args)
+        ref.load_state_dict(sd, strict=True, device=_dev())
+        pc = synthetic_pc_normal(1, first=3).to(_dev())
+        a, b = model(pc), ref(pc)
+        assert torch.equal(torch.nan_to_num(a, nan=7.0), torch.nan_to_num(b, nan=7.0))
+        assert torch.equal(model.last_ids, ref.last_ids)
+        # plain HF spelling of the BERT layers
+        hf = {k: v for k, v in sd.items() if not k.startswith("tokenizer.decoder.layer.")}
+        w = 768
+        for i in range(6):
+            q, o = f"tokenizer.decoder.layer.{i}", f"tokenizer.decoder.layer.{i}"
+            iw, ib = sd[f"{q}.in_proj_weight"], sd[f"{q}.in_proj_bias"]
+            for j, nm in enumerate(("query", "key", "value")):
+                hf[f"{o}.attention.self.{nm}.weight"] = iw[j * w:(j + 1) * w].clone()
+                hf[f"{o}.attention.self.{nm}.bias"] = ib[j * w:(j + 1) * w].clone()
+            for src, dst in (("out_proj", "attention.output.dense"), ("linear1", "intermediate.dense"),
+                             ("linear2", "output.dense")):
+                hf[f"{o}.{dst}.weight"], hf[f"{o}.{dst}.bias"] = sd[f"{q}.{src}_weight"], sd[f"{q}.{src}_bias"]
+            for src, dst in (("norm1", "attention.output.LayerNorm"), ("norm2", "output.LayerNorm")):
+                hf[f"{o}.{dst}.weight"], hf[f"{o}.{dst}.bias"] = sd[f"{q}.{src}_weight"], sd[f"{q}.{src}_bias"]
+        args2 = argparse.Namespace(**{**vars(args), "pretrained_weights": str(tmp_path / "hf_names.safetensors")})
+        save_file({k: v.contiguous() for k, v in hf.items()}, args2.pretrained_weights)
+        model2 = cli.load_model(args2, device=_dev())
+        assert torch.equal(torch.nan_to_num(model2(pc), nan=7.0), torch.nan_to_num(b, nan=7.0))
+        # strictness
+        broken = dict(sd)
+        broken.pop("cond_proj.weight")
+        with pytest.raises(RuntimeError, match="cond_proj.weight"):
+            MeshAnything(args).load_state_dict(broken, strict=True, device=_dev())
+        extra = dict(sd)
+        extra["not.a.key"] = torch.zeros(1)
+        with pytest.raises(RuntimeError, match="not.a.key"):
+            MeshAnything(args).load_state_dict(extra, strict=True, device=_dev())
+    finally:
+        MeshAnything.expected_keys = orig_expected
+
+
+@gpu
+def test_config1_mouse_example_when_present():
+    """BASELINE configs[0] plumbing: /root/reference/pc_examples/mouse.npy (exists in the development container only)
+    through the reference's own loading steps (main.py:22-27,47-56: subsample to 4096 with np.random.choice under seed 0,
+    normalise, check the normals) and MeshAnything.forward at a 64-face cap."""
+    import os
+    import numpy as np
+    path = "/root/reference/pc_examples/mouse.npy"
+    if not os.path.exists(path):
+        pytest.skip("the reference tree is not on this box")
+    from meshanything_b200.inputs import normalize_pc_normal
+    from MeshAnything.models.meshanything import MeshAnything
+    np.random.seed(0)
+    cur = np.load(path)
+    assert cur.shape[0] >= 4096
+    cur = cur[np.random.choice(cur.shape[0], 4096, replace=False)]
+    pc = normalize_pc_normal(cur)
+    args = argparse.Namespace(llm="facebook/opt-350m", codebook_size=8192, codebook_dim=1024, n_max_triangles=64, seed=0)
+    model = MeshAnything(args)
+    model.load_state_dict(ck.synthetic_state_dict(0), strict=True, device=_dev())
+    out = model(torch.from_numpy(pc[None]).to(_dev()))
+    assert out.shape == (1, 64, 3, 3)
+    ok = ~torch.isnan(out)
+    assert ok.any() and float(out[ok].min()) >= -0.5 and float(out[ok].max()) < 0.5

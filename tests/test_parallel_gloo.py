@@ -26,7 +26,9 @@ def _worker(rank, world, port, q):
     sd = ck.make_state_dict(specs, 0) if r == 0 else None
     out = parallel.broadcast_state_dict(sd, specs, torch.device("cpu"))
     ref = ck.make_state_dict(specs, 0)
-    ok = all(torch.equal(out[k], ref[k]) for k in specs)
+    # Linear parameters travel as fp16 (what the arenas keep), everything else as fp32, bit for bit
+    ok = all(torch.equal(out[k], ref[k].half() if ck.consumed_as_fp16(k) else ref[k]) for k in specs)
+    ok = ok and any(out[k].dtype == torch.float16 for k in specs) and any(out[k].dtype == torch.float32 for k in specs)
     lo, hi = parallel.shard_range(11, r, w)
     q.put((r, ok, lo, hi))
     dist.barrier()

@@ -4,8 +4,8 @@
 
 Times, with CUDA events on the launching stream (20 launches after 5 warm-ups, inputs larger than L2 or rotated):
   * attention_kernel (ma_attention_f16) for B rows x 16 heads at several context lengths -> achieved KV GB/s;
-  * the canonical fp32-FMA GEMM (ma_linear_f16) and the tcgen05 GEMM (ma_linear_tc_f16) at M = B for the five
-    decoder shapes -> us per call, weight GB/s, TFLOP/s.
+  * the canonical fp32-FMA GEMM (ma_linear_f16), the tiled tcgen05 GEMM (ma_linear_tc_f16) and the weight-streaming
+    tcgen05 GEMM (ma_linear_ws_f16) at M = B for the five decoder shapes -> us per call, weight GB/s, TFLOP/s.
 Prints one JSON object (committed under profiles/ by hand)."""
 import argparse
 import ctypes as C
@@ -78,7 +78,7 @@ def main():
                     f(w, b, x)
             return g
         rec = {"name": name, "N": N, "K": K}
-        for tag, f in (("canon", capi.linear_f16), ("tcgen05", capi.linear_tc_f16)):
+        for tag, f in (("canon", capi.linear_f16), ("tcgen05", capi.linear_tc_f16), ("tcgen05_ws", capi.linear_ws_f16)):
             try:
                 g = graph_of(f)
                 us = timed(g.replay, n=10, warm=2) / 24
