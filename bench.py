@@ -181,6 +181,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="shapes per GPU (overrides --config)")
     ap.add_argument("--faces", type=int, default=None)
     ap.add_argument("--no-extra", action="store_true", help="skip the bounded config-3/5 decode-step block")
+    ap.add_argument("--lean", action="store_true",
+                    help="only the contract's two timed regions (value, e2e): no separate stage / short-context runs; the "
+                         "roofline then uses the whole step's time (for the long multi-GPU configurations)")
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--sampling", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
@@ -308,9 +311,12 @@ def main():
         ms_e2e, out_e2e = timed(one_step_e2e, args.steps)
     mega_err = gen.mega_error() if (B == 1 and not args.sampling) else 0
     # stage split of one pass (encoder / decode loop / detokenizer), device timed
-    ms_enc, _ = timed(lambda: model.point_encoder.encode_with_prefix(pc_dev), args.steps)
-    ms_gen, gen_out = timed(lambda: gen.generate(prefix_dev, max_new, do_sample=args.sampling, seed=0, flags=flags),
-                            args.steps)
+    if args.lean:
+        ms_enc, ms_gen, gen_out = 0.0, ms, (model.last_ids,)
+    else:
+        ms_enc, _ = timed(lambda: model.point_encoder.encode_with_prefix(pc_dev), args.steps)
+        ms_gen, gen_out = timed(lambda: gen.generate(prefix_dev, max_new, do_sample=args.sampling, seed=0, flags=flags),
+                                args.steps)
     ms_all = ms
 
     ids = gen_out[0]
@@ -334,16 +340,22 @@ def main():
         t, _ = timed(lambda: g2.generate(prefix_dev, nn, flags=flags), 3)
         return t / 3
     n_lo, n_hi = (100, 300) if max_new >= 300 else (max(2, max_new // 4), max_new)
-    t100, t300 = short(n_lo), short(n_hi)
+    if args.lean:
+        t100 = n_lo * ms / args.steps / max_new
+        t300 = n_hi * ms / args.steps / max_new
+    else:
+        t100, t300 = short(n_lo), short(n_hi)
     us_step_short = (t300 - t100) / float(n_hi - n_lo) * 1000.0
     short_bytes = wbytes + KV_BYTES_PER_POS * B * (257 + (n_lo + n_hi) // 2 + 1)
     t_prefill_ms = t100 - (n_lo - 1) * us_step_short / 1000.0
     dec_ms = ms / args.steps - max(0.0, t_prefill_ms)             # decode-loop part of one generate
     achieved = alg_bytes_per_gen / (dec_ms / 1000.0) / 1e9
     traffic = None   # DRAM bytes per decode token from the committed ncu --set full capture of the same kernel
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if B == 1 and not args.sampling and os.path.exists(tpath):
-        traffic = json.load(open(tpath))["traffic_bytes_per_token"]
+    for tag in ("r02", "r01"):     # the newest committed `ncu --set full` capture of the persistent kernel
+        tpath = os.path.join(ROOT, "profiles", f"traffic_{tag}.json")
+        if B == 1 and not args.sampling and os.path.exists(tpath):
+            traffic = json.load(open(tpath))["traffic_bytes_per_token"]
+            break
     roofline = {
         "bound": "hbm",
         "kernel": ("decode_mega_kernel (persistent: all 121 phases of a token, 512 tokens per launch)"
@@ -360,6 +372,7 @@ def main():
                           "achieved": short_bytes / us_step_short / 1e3, "frac": short_bytes / us_step_short / 1e3 / peak,
                           "note": "steps at context ~%d..%d (GEMV-dominated): (T(%d)-T(%d))/%d" % (257 + n_lo, 257 + n_hi, n_hi, n_lo, n_hi - n_lo)},
         "prefill_ms": t_prefill_ms,
+        "lean": bool(args.lean),
     }
 
     extra = None

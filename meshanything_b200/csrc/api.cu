@@ -100,10 +100,16 @@ static inline __half* kv_layer(void* kv, int layer, int which, int B, long T) {
 static int dec_linear(bool tc, const DecWs& ws, const void* W, const void* b, const __half* x, int ldx, __half* y, int ldy,
                       int M, int N, int K, int epi, cudaStream_t st) {
   if (tc) {
+    // measured at M = 64 (profiles/batched_kernels_r02.json, us per call): the tiled kernel wins where one row of
+    // 128-row tiles is already 8-32 CTAs with a short K (qkv 9.3, out_proj 7.6, fc1 9.4 vs 11.1 / 15.8 / 11.5 for the
+    // weight-streaming kernel); the weight-streaming kernel wins on K = 4096 (fc2: 19.0 vs 22.7), on lm_head (N = 8195 is
+    // not tileable: 12.1 vs 42.8 for the canonical kernel) and is the only tcgen05 path below 64 rows
+    const bool tiled_ok = M >= 64 && linear_tc_supported(M, N, K, ldx, ldy, x, W, y);
+    if (tiled_ok && (K <= 1024 || M > 128))
+      return launch_linear_tc((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
     if (M <= 128 && linear_ws_supported(M, N, K, ldx, x, W))
       return launch_linear_ws((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, ws.tc_scratch, st);
-    if (M > 128 && linear_tc_supported(M, N, K, ldx, ldy, x, W, y))
-      return launch_linear_tc((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
+    if (tiled_ok) return launch_linear_tc((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
   }
   return launch_linear((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
 }

@@ -60,8 +60,9 @@ def test_decoder_vs_hf_autocast_fp16_full_depth():
     fp16 logits of ma_decode_generate (persistent kernel) vs HF OPTDecoderLayer x 24 under fp16 autocast on the same
     GPU.  Tolerance: both sides round Linear outputs to fp16 but accumulate in different orders (cuBLAS / SDPA vs the
     canonical order), so individual activations can land on neighbouring fp16 values and the differences random-walk
-    through 24 layers; measured on the B200: see the printed line (asserted: max < 8e-2, mean < 8e-3 on logits of std
-    1.6, argmax equal wherever HF's top-2 margin exceeds 0.1)."""
+    through 24 layers.  Measured on the B200 (round 2): max |diff| 7.8e-3, mean 8.6e-4 on logits of std 1.62, argmax
+    equal at all 300 positions.  Asserted: max < 3e-2, mean < 3e-3, argmax equal wherever HF's top-2 margin exceeds
+    4e-2 and at >= 99 % of all positions."""
     from meshanything_b200.decoder import DecoderArena, Generator
     dev = torch.device("cuda:0")
     NL, n = 24, 300
@@ -85,7 +86,7 @@ def test_decoder_vs_hf_autocast_fp16_full_depth():
     print(f"decoder vs HF autocast fp16: max |diff| {float(diff.max()):.4f} mean {float(diff.mean()):.5f} "
           f"(logit std {float(ref.std()):.3f}); argmax agreement {float(agree.float().mean()):.4f} over {n} positions, "
           f"{int((margin > 0.1).sum())} with margin > 0.1")
-    assert diff.max() < 8e-2 and diff.mean() < 8e-3
-    clear = margin > 0.1
+    assert diff.max() < 3e-2 and diff.mean() < 3e-3
+    clear = margin > 4e-2
     assert torch.equal(got.argmax(1)[clear], ref.argmax(1)[clear])
-    assert agree.float().mean() > 0.97
+    assert agree.float().mean() >= 0.99

@@ -148,10 +148,45 @@ def test_forward_drop_in(full):
         assert ids[b].tolist()[:len(ref)] == ref
     # detokenizer leg on the same ids
     with torch.no_grad():
-        rc = torch_ref.detokenize(full, torch_ref.postprocess_ids(ids.long(), F_SMALL), pf.cpu())
+        rc, rlog = torch_ref.detokenize(full, torch_ref.postprocess_ids(ids.long(), F_SMALL), pf.cpu(), return_logits=True)
     assert torch.equal(torch.isnan(out.cpu()), torch.isnan(rc))
     valid = ~torch.isnan(rc)
-    assert (out.cpu()[valid] == rc[valid]).float().mean() > 0.9
+    same = out.cpu()[valid] == rc[valid]
+    top2 = torch.topk(rlog, 2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1]).view(2, F_SMALL, 3, 3)[valid]
+    assert same.float().mean() > 0.97 and (margin[~same] < 0.08).all()      # the rule of the dedicated detokenizer test
+    # END TO END with the encoder in the loop: greedy ids from the GPU encoder's prefix (within 1e-2 of the fp32
+    # reference, test_encoder_vs_fp32_reference) against the oracle's ids from the fp32 REFERENCE prefix.  A free-running
+    # greedy decode amplifies any logit difference at a near-tie, so what is asserted is the teacher-forced view: along
+    # the reference path the GPU logits stay close and the argmax agrees wherever the margin is clear.  The first
+    # divergence step and the agreement rate of the free-running ids are reported.
+    from meshanything_b200.decoder import Generator
+    n64 = 9 * 64 + 2
+    with torch.no_grad():
+        _, ref_prefix = torch_ref.encoder_forward(full, pc[:1])
+    oracle64 = OracleDecoder(full, 24, 257 + n64)
+    ref_ids, ref_logits = oracle64.generate(ref_prefix[0], n64, keep_logits=True)
+    g64 = Generator(model._dec, 1, 257 + n64)
+    got_ids, _ = g64.generate(prefix[:1], n64)
+    got_ids = got_ids[0].cpu().tolist()
+    first_div = next((i for i, (a, b) in enumerate(zip(got_ids, ref_ids)) if a != b), len(ref_ids))
+    agree = sum(a == b for a, b in zip(got_ids, ref_ids)) / len(ref_ids)
+    forced = torch.tensor([ref_ids + [2] * (n64 - len(ref_ids))], dtype=torch.int32)
+    _, _, tf = g64.generate(prefix[:1], n64, forced_ids=forced, want_logits=True, eos_id=-1)
+    rl = torch.stack(ref_logits).float()
+    gl = tf[:len(ref_logits), 0].cpu().float()
+    d = (gl - rl).abs()
+    t2 = torch.topk(rl, 2, dim=1).values
+    clear = (t2[:, 0] - t2[:, 1]) > 0.25
+    print("end to end (GPU encoder prefix vs fp32 reference prefix, F=64): first divergence at step %d of %d, free-running "
+          "agreement %.3f; teacher-forced logits max |diff| %.4f mean %.5f, argmax agreement %.4f (%d positions with margin > 0.25)"
+          % (first_div, len(ref_ids), agree, float(d.max()), float(d.mean()),
+             float((gl.argmax(1) == rl.argmax(1)).float().mean()), int(clear.sum())))
+    # measured on the B200 (round 2): first divergence at step 95 of 578, free-running agreement 0.972; teacher-forced
+    # max |diff| 7.8e-3, mean 1.1e-3, argmax agreement 0.995 (the 3 disagreeing positions have margins below 0.01)
+    assert first_div >= 1
+    assert d.max() < 5e-2 and d.mean() < 5e-3
+    assert torch.equal(gl.argmax(1)[clear], rl.argmax(1)[clear])
     # one shape alone, and sampling mode
     out1 = model(pc[:1].to(_dev()))
     assert torch.equal(torch.nan_to_num(out1[0]), torch.nan_to_num(out[0]))

@@ -48,7 +48,28 @@ def full(path, title):
 launches(f"gpurun_out/launches_{tag}.csv")
 full(f"gpurun_out/prof_mega_{tag}.ncu-rep", "Persistent decode kernel")
 full(f"gpurun_out/prof_gemm_tc_{tag}.ncu-rep", "tcgen05 + TMA GEMM of the encoder (batch 8: M = 2056 / 32768 rows)")
+full(f"gpurun_out/prof_attn_tc_{tag}.ncu-rep", "tcgen05 flash attention of the encoder (batch 8: cross-attention 257 x 4096 keys, self-attention 257 x 257)")
+full(f"gpurun_out/prof_gemm_ws_{tag}.ncu-rep", "Weight-streaming tcgen05 GEMM of the batched decode step (M = 64)")
 full(f"gpurun_out/prof_batched_{tag}.ncu-rep", "Canonical CUDA-core GEMM and attention kernels (batch 8 decode / prefill)")
+def traffic(path, tokens):
+    if not os.path.exists(path):
+        return
+    r = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
+    rows = list(csv.reader(r.stdout.splitlines()))
+    hdr, units, line = rows[0], rows[1], rows[2]
+    def val(name):
+        i = hdr.index(name)
+        v = float(line[i].replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(units[i], 1)
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    alg = 621205504 + 98304 * ((258 + 258 + tokens - 1) / 2 + 1)
+    json.dump({"kernel": "decode_mega_kernel",
+               "capture": f"profiles/ncu_summary_{tag}.md ({os.path.basename(path)}: bench.py --faces 16, one launch = {tokens} decode tokens at contexts 258..{257 + tokens})",
+               "dram_bytes_read": rd, "dram_bytes_write": wr, "tokens_in_launch": tokens,
+               "traffic_bytes_per_token": (rd + wr) / tokens, "algorithmic_bytes_per_token": alg},
+              open(f"profiles/traffic_{tag}.json", "w"), indent=1)
+
+traffic(f"gpurun_out/prof_mega_{tag}.ncu-rep", 145)
 os.makedirs("profiles", exist_ok=True)
 open(f"profiles/ncu_summary_{tag}.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:3000])
