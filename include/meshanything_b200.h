@@ -132,6 +132,10 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
  *                           synchronising call; the scheduler calls it every few dozen steps).
  * Every sequence gets the ids a solo ma_decode_generate would give it (batch-invariant arithmetic). */
 int ma_decode_slots_init(int B, int tmax, int pad_id, void* ws, void* stream);
+/* Sampling only: the Philox stream of the sequence about to be prefilled into `slot` (e.g. its index in the queue).
+ * Draws are keyed by (seed, stream, token index), so shapes that pass through the same slot are independent and a
+ * shape's samples do not depend on the slot it lands in.  Call before ma_decode_slot_prefill; default stream 0. */
+int ma_decode_slot_stream(int slot, int B, int tmax, int stream_id, void* ws, void* stream);
 /* Measurement hook (bench.py, tools/): declares every slot live at cached position `pos` having generated `gen` tokens,
  * last token `tok`, WITHOUT running the steps that lead there -- the KV cache keeps whatever it holds (the caller
  * zero-fills it).  Lets a bounded number of ma_decode_slots_step calls be timed at a chosen context length. */

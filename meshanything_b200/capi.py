@@ -43,7 +43,7 @@ EXPORTS = [
     "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores", "ma_sample_tokens",
     "ma_attention_tc_f16", "ma_transpose_heads_f16",
     "ma_decode_slots_init", "ma_decode_slot_prefill", "ma_decode_slots_step", "ma_decode_slots_poll",
-    "ma_mega_set_debug", "ma_decode_slots_seek", "ma_linear_ws_scratch_bytes", "ma_linear_ws_f16",
+    "ma_mega_set_debug", "ma_decode_slots_seek", "ma_decode_slot_stream", "ma_linear_ws_scratch_bytes", "ma_linear_ws_f16",
     "ma_sample_surface_workspace_bytes", "ma_sample_surface", "ma_tensor_core_linear_counts",
 ]
 
@@ -86,6 +86,7 @@ def lib():
                                       C.c_float, _vp, C.c_int, _vp]
     L.ma_transpose_heads_f16.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _vp, _vp]
     L.ma_decode_slots_init.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.ma_decode_slot_stream.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.ma_decode_slots_seek.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.ma_decode_slot_prefill.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(Sampling), C.c_int, C.c_int, _vp, _vp, _vp, _vp]

@@ -78,6 +78,7 @@ static DecWs carve(void* base, int B, int tmax, int vocab) {
   w.s.tok = (int*)take((size_t)B * 4);
   w.s.finished = (int*)take((size_t)B * 4);
   w.s.lens = (int*)take((size_t)B * 4);
+  w.s.sid = (int*)take((size_t)B * 4);
   w.all_done = (int*)take(256);
   w.attn_scratch_bytes = attention_scratch_bytes((int)B, NHEAD, tmax);
   w.attn_scratch = take(w.attn_scratch_bytes);
@@ -414,7 +415,7 @@ int ma_decode_generate(const ma_decoder_weights* w, const float* prefix, int B, 
       key.w = w; key.kv = kv; key.ws = ws_; key.out_ids = out_ids; key.forced = forced_ids; key.logits_out = logits_out;
       key.B = B; key.tmax = tmax; key.max_new = max_new; key.bucket = bucket; key.flags = flags;
       key.do_sample = sa.do_sample; key.top_k = sa.top_k; key.eos = eos_id; key.pad = pad_id; key.top_p = sa.top_p;
-      key.seed = sa.seed;
+      key.seed = sa.do_sample ? sa.seed : 0;   // greedy graphs do not depend on the seed
       key.whash = whash;
       if (launch_cached_graph(key, st, enqueue)) return 1;
     }
@@ -472,8 +473,21 @@ int ma_decode_slots_init(int B, int tmax, int pad_id, void* ws_, void* stream) {
   // every slot starts free: finished, nothing generated, a valid (pad) token at a valid position
   if (launch_fill_i32(ws.s.pos, PREFIX, B, st) || launch_fill_i32(ws.s.gen, 0, B, st) ||
       launch_fill_i32(ws.s.tok, pad_id, B, st) || launch_fill_i32(ws.s.finished, 1, B, st) ||
-      launch_fill_i32(ws.s.lens, 0, B, st)) return 1;
+      launch_fill_i32(ws.s.lens, 0, B, st) || launch_fill_i32(ws.s.sid, 0, B, st)) return 1;
   return slots_leave(stream, "ma_decode_slots_init");
+}
+
+int ma_decode_slot_stream(int slot, int B, int tmax, int stream_id, void* ws_, void* stream) {
+  if (!ws_ || slot < 0 || slot >= B) {
+    set_error("ma_decode_slot_stream: bad arguments (slot %d of %d)", slot, B);
+    return 1;
+  }
+  std::lock_guard<std::mutex> lock(g_mu);
+  cudaStream_t st;
+  if (slots_enter(stream, &st)) return 1;
+  DecWs ws = carve(ws_, B, tmax, 8195 + 61);
+  if (launch_fill_i32(ws.s.sid + slot, stream_id, 1, st)) return 1;
+  return slots_leave(stream, "ma_decode_slot_stream");
 }
 
 int ma_decode_slots_seek(int B, int tmax, int pos, int gen, int tok, void* ws_, void* stream) {
@@ -552,7 +566,7 @@ int ma_decode_slots_step(const ma_decoder_weights* w, int B, int tmax, int max_n
       key.w = w; key.kv = kv; key.ws = ws_; key.out_ids = out_ids;
       key.B = B; key.tmax = tmax; key.max_new = max_new; key.bucket = bucket; key.flags = flags; key.mode = 1;
       key.do_sample = sa.do_sample; key.top_k = sa.top_k; key.eos = eos_id; key.pad = pad_id; key.top_p = sa.top_p;
-      key.seed = sa.seed; key.whash = whash;
+      key.seed = sa.do_sample ? sa.seed : 0;   // greedy graphs do not depend on the seed key.whash = whash;
       if (launch_cached_graph(key, st, enqueue)) return 1;
     }
   }

@@ -58,7 +58,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(AttnArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, grp = lane >> 3, li = lane & 7;
 
   if (!a.decode_prefetch) pdl_wait();  // everything this kernel reads may come from the previous kernel
-  const int n = a.nkeys[m];
+  // never more keys than this launch has chunks for: a frozen cache slot (continuous batching) keeps an old, possibly
+  // larger position than the bucket the grid was sized from; its output is discarded anyway
+  const int n = min(a.nkeys[m], a.max_chunks * MA_ATTN_CHUNK);
   if (c * MA_ATTN_CHUNK >= n) return;
   const int len = min(MA_ATTN_CHUNK, n - c * MA_ATTN_CHUNK);
   const int nch = (n + MA_ATTN_CHUNK - 1) / MA_ATTN_CHUNK;

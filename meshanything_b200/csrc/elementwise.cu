@@ -354,7 +354,9 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
         for (int j = 0; j < keep; j++) a.support_out[(long)b * KEEP_MAX + j] = sorti[j];
       float ksum = 0.0f;
       for (int j = 0; j < keep; j++) ksum = fadd(ksum, keepv[j]);
-      const float u = fmul(philox_uniform(a.seed, (uint32_t)b, (uint32_t)gen), ksum);
+      // stream = the row, or (continuous batching) the queue index of the sequence that occupies the slot
+      const uint32_t stream = (a.slots && a.s.sid) ? (uint32_t)a.s.sid[b] : (uint32_t)b;
+      const float u = fmul(philox_uniform(a.seed, stream, (uint32_t)gen), ksum);
       float acc = 0.0f;
       tok = sorti[keep - 1];
       for (int j = 0; j < keep; j++) {

@@ -22,6 +22,8 @@ struct SeqState {
   int* tok;       // last generated token (input of the next step)
   int* finished;  // eos seen
   int* lens;      // tokens up to and including eos (or gen)
+  int* sid;       // continuous batching: Philox stream of the sequence in this slot (its index in the queue), so that
+                  // two shapes that pass through the same slot do not draw the same uniforms
 };
 
 void set_error(const char* fmt, ...);

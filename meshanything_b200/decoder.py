@@ -107,8 +107,11 @@ class Generator:
         assert prefix.is_cuda and prefix.dtype == torch.float32
         prefix = prefix.contiguous()
         dev = prefix.device
-        ids = torch.empty((B, max_new_tokens), dtype=torch.int32, device=dev)
-        lens = torch.empty((B,), dtype=torch.int32, device=dev)
+        # persistent output buffers: stable pointers keep the per-step CUDA graphs of the library reusable across calls
+        if getattr(self, "_ids_buf", None) is None or self._ids_buf.shape != (B, max_new_tokens):
+            self._ids_buf = torch.empty((B, max_new_tokens), dtype=torch.int32, device=dev)
+            self._lens_buf = torch.empty((B,), dtype=torch.int32, device=dev)
+        ids, lens = self._ids_buf, self._lens_buf
         logits = None
         if want_logits:
             logits = torch.zeros((max_new_tokens, B, self.arena.c.vocab), dtype=torch.float16, device=dev)
@@ -120,6 +123,7 @@ class Generator:
                                            capi.ptr(ids), capi.ptr(lens), capi.ptr(forced_ids), capi.ptr(logits),
                                            flags, capi.stream_ptr())
         capi.check(rc, "ma_decode_generate")
+        ids, lens = ids.clone(), lens.clone()          # the caller owns what it gets; the buffers are reused
         self._last_lens = lens
         return (ids, lens, logits) if want_logits else (ids, lens)
 

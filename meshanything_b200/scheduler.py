@@ -121,6 +121,7 @@ class SlotEngine:
 
     def reset(self) -> None:
         """Every slot free again (call between queues; sequences still in flight are dropped)."""
+        self._n_prefills = 0
         capi.check(capi.lib().ma_decode_slots_init(self.B, self.tmax, self.pad_id, capi.ptr(self.ws),
                                                    capi.stream_ptr()), "ma_decode_slots_init")
 
@@ -128,6 +129,10 @@ class SlotEngine:
         prefix = self.to_prefix(payload) if self.to_prefix is not None else payload
         assert prefix.is_cuda and prefix.dtype == torch.float32
         prefix = prefix.reshape(DEC.cond_length, DEC.hidden).contiguous()
+        if self.samp.do_sample:      # the k-th shape of this run draws from Philox stream k, whatever slot it lands in
+            capi.check(capi.lib().ma_decode_slot_stream(slot, self.B, self.tmax, self._n_prefills, capi.ptr(self.ws),
+                                                        capi.stream_ptr()), "ma_decode_slot_stream")
+        self._n_prefills += 1
         capi.check(capi.lib().ma_decode_slot_prefill(C.byref(self.arena.c), capi.ptr(prefix), slot, self.B, self.tmax,
                                                      self.max_new, C.byref(self.samp), self.eos_id, self.pad_id,
                                                      capi.ptr(self.kv), capi.ptr(self.ws), capi.ptr(self.ids),

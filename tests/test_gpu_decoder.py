@@ -339,3 +339,27 @@ def test_continuous_batching_equals_solo_generation(small, slots, poll_every, fl
     for i in range(NP):
         assert got[i] == solo[i], (i, len(got[i]), len(solo[i]))
     assert sched.stats.prefills == NP
+
+
+@gpu
+def test_continuous_batching_sampling_streams_follow_the_queue(small):
+    """Sampling under continuous batching: draws are keyed by (seed, index of the shape in the queue, token index), not
+    by the cache slot.  The same prefix queued three times through ONE slot must give three different samples (a
+    slot-keyed stream would repeat the first), and a queue's results must not depend on how many slots it ran through
+    (2 vs 3 slots: same kernels, same per-row arithmetic, different slot assignment)."""
+    from meshanything_b200.scheduler import SlotEngine, SlotScheduler
+    _, arena, _ = small
+    n = 24
+    p = random_prefix(2, seed=31).to(_dev())
+
+    def run(queue, slots):
+        eng = SlotEngine(arena, slots, 257 + n, n, do_sample=True, seed=11, eos_id=-1)
+        sched = SlotScheduler(eng, slots, n, poll_every=5)
+        got = {idx: ids.cpu().tolist() for idx, ids in sched.run(queue)}
+        return [got[i] for i in range(len(queue))]
+
+    one = run([p[0], p[0], p[0]], 1)
+    assert one[0] != one[1] and one[1] != one[2] and one[0] != one[2]
+    assert run([p[0], p[0], p[0]], 1) == one
+    q = [p[0], p[1], p[0], p[1], p[0]]
+    assert run(q, 2) == run(q, 3)
