@@ -63,6 +63,13 @@ size_t ma_attention_scratch_bytes(int M, int H, int max_keys);
 int ma_attention_f16(const void* q, int ldq, const void* K, const void* V, long T, int H, const int* slots,
                      const int* nkeys, int max_keys, int M, float scale, void* out, int ldo, void* scratch,
                      void* stream);
+/* One decode step of a batch: row m = cache slot m, 16 heads.  qkv [M][ldq] fp16 holds q | k | v of the current token
+ * (columns 0.., 1024.., 2048..); the k / v rows are appended to the cache at position nkeys[m]-1 and row m attends keys
+ * [0, nkeys[m]) -- the same arithmetic as ma_attention_f16, bit for bit, as one persistent pipelined kernel
+ * (attention_stream.cu).  This is the flash_attn_func call of OptFlashAttention2 on the decode path plus the cache
+ * update of transformers' OPT attention (past_key_value concat).  scratch as for ma_attention_f16 with H = 16. */
+int ma_attention_decode_f16(const void* qkv, int ldq, void* K, void* V, long T, const int* nkeys, int max_keys, int M,
+                            float scale, void* out, int ldo, void* scratch, void* stream);
 
 /* ---- ShapeOPT decoder (shape_opt.py:188-460 + HF generate) --------------------------------- */
 
@@ -177,6 +184,9 @@ int ma_linear_tc_f16(const void* W, const void* bias, const void* x, int ldx, vo
  * OPTDecoderLayer for a decode step of a batch (shape_opt.py:403-410).  scratch: ma_linear_ws_scratch_bytes() bytes,
  * zero-filled once by the caller.  Hardware accumulation order: compared under a tolerance. */
 size_t ma_linear_ws_scratch_bytes(void);
+/* 1 (default): the K slices of a row block are a thread-block cluster and are added over distributed shared memory;
+ * 0: partial tiles through L2 and an atomic ticket (kept for A/B timing).  Both add the slices in slice order. */
+void ma_linear_ws_set_mode(int cluster);
 int ma_linear_ws_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
                      int epilogue, void* scratch, void* stream);
 /* 0: canonical CUDA-core kernels everywhere; 1: encoder / detokenizer GEMMs on the tensor cores; 2: their attention

@@ -38,12 +38,12 @@ _lib = None
 
 EXPORTS = [
     "ma_abi_version", "ma_last_error", "ma_launch_count", "ma_linear_f16", "ma_layernorm",
-    "ma_attention_scratch_bytes", "ma_attention_f16", "ma_kv_cache_bytes", "ma_decoder_workspace_bytes",
+    "ma_attention_scratch_bytes", "ma_attention_f16", "ma_attention_decode_f16", "ma_kv_cache_bytes", "ma_decoder_workspace_bytes",
     "ma_decode_generate", "ma_decoder_debug", "ma_encoder_workspace_bytes", "ma_encoder_forward",
     "ma_detokenize_workspace_bytes", "ma_detokenize", "ma_linear_tc_f16", "ma_set_tensor_cores", "ma_sample_tokens",
     "ma_attention_tc_f16", "ma_transpose_heads_f16",
     "ma_decode_slots_init", "ma_decode_slot_prefill", "ma_decode_slots_step", "ma_decode_slots_poll",
-    "ma_mega_set_debug", "ma_decode_slots_seek", "ma_decode_slot_stream", "ma_linear_ws_scratch_bytes", "ma_linear_ws_f16",
+    "ma_mega_set_debug", "ma_linear_ws_set_mode", "ma_decode_slots_seek", "ma_decode_slot_stream", "ma_linear_ws_scratch_bytes", "ma_linear_ws_f16",
     "ma_sample_surface_workspace_bytes", "ma_sample_surface", "ma_tensor_core_linear_counts",
 ]
 
@@ -82,10 +82,14 @@ def lib():
     L.ma_decode_generate.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.POINTER(Sampling),
                                      C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp]
     L.ma_sample_tokens.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(Sampling), _vp, _vp, _vp]
+    L.ma_attention_decode_f16.argtypes = [_vp, C.c_int, _vp, _vp, C.c_long, _vp, C.c_int, C.c_int, C.c_float, _vp, C.c_int,
+                                          _vp, _vp]
     L.ma_attention_tc_f16.argtypes = [_vp, C.c_int, _vp, _vp, C.c_long, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, _vp, C.c_int, _vp]
     L.ma_transpose_heads_f16.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_long, C.c_int, _vp, _vp]
     L.ma_decode_slots_init.argtypes = [C.c_int, C.c_int, C.c_int, _vp, _vp]
+    L.ma_linear_ws_set_mode.argtypes = [C.c_int]
+    L.ma_linear_ws_set_mode.restype = None
     L.ma_decode_slot_stream.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.ma_decode_slots_seek.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.ma_decode_slot_prefill.argtypes = [C.POINTER(DecoderWeights), _vp, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -251,6 +255,23 @@ def layernorm(x: Optional[torch.Tensor], res16: Optional[torch.Tensor], gamma: t
     check(lib().ma_layernorm(ptr(x), ptr(res16), ptr(gamma), ptr(beta), eps, M, W, ptr(o32), ptr(o16), stream_ptr()),
           "ma_layernorm")
     return o32, o16
+
+
+def attention_decode_f16(qkv: torch.Tensor, k: torch.Tensor, v: torch.Tensor, nkeys: torch.Tensor,
+                         scale: float = 0.125) -> torch.Tensor:
+    """qkv [M,3072] fp16 (q | k | v of the current token); k,v [M,16,T,64] fp16 caches (updated in place at nkeys-1);
+    nkeys int32 [M] counts the current token.  Returns the attention output [M,1024] fp16."""
+    _need_cuda(qkv, k, v, nkeys)
+    M = qkv.shape[0]
+    assert qkv.shape[1] == 3072 and qkv.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    assert k.shape[0] == M and k.shape[1] == 16 and k.shape[3] == 64
+    T = k.shape[2]
+    max_keys = int(nkeys.max().item())
+    scratch = torch.zeros(lib().ma_attention_scratch_bytes(M, 16, max_keys), dtype=torch.uint8, device=qkv.device)
+    out = torch.empty((M, 1024), dtype=torch.float16, device=qkv.device)
+    check(lib().ma_attention_decode_f16(ptr(qkv), 3072, ptr(k), ptr(v), T, ptr(nkeys), max_keys, M, scale, ptr(out),
+                                        1024, ptr(scratch), stream_ptr()), "ma_attention_decode_f16")
+    return out
 
 
 def attention_f16(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, nkeys: torch.Tensor,

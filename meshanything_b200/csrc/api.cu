@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libmeshanything_b200.so (include/meshanything_b200.h) and the host side
 // of generate(): prefill, then one CUDA graph launch per token.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -95,20 +96,26 @@ static inline __half* kv_layer(void* kv, int layer, int which, int B, long T) {
   return (__half*)kv + ((size_t)(layer * 2 + which) * B) * NHEAD * T * HD;
 }
 
+// MA_B200_NO_STREAM_ATTN=1: decode steps of a batch use kv_append_kernel + attention_kernel (one CTA per chunk) instead
+// of attention_stream_kernel -- same bits, kept for A/B timing (tools/bench_batched.py)
+static const bool g_no_stream_attn = [] {
+  const char* e = getenv("MA_B200_NO_STREAM_ATTN");
+  return e && e[0] == '1';
+}();
+
 // One pass of the 24 layers over M rows (general batched kernels).
 // y = act(x W^T + b) for M rows of the decoder: the canonical kernel, or (tc) the tensor cores -- the weight-streaming
 // tcgen05 GEMM for M <= 128 rows (decode steps), the tiled tcgen05 GEMM for the 257-row prefill passes
 static int dec_linear(bool tc, const DecWs& ws, const void* W, const void* b, const __half* x, int ldx, __half* y, int ldy,
                       int M, int N, int K, int epi, cudaStream_t st) {
   if (tc) {
-    // measured at M = 64 (profiles/batched_kernels_r02.json, us per call): the tiled kernel wins where one row of
-    // 128-row tiles is already 8-32 CTAs with a short K (qkv 9.3, out_proj 7.6, fc1 9.4 vs 11.1 / 15.8 / 11.5 for the
-    // weight-streaming kernel); the weight-streaming kernel wins on K = 4096 (fc2: 19.0 vs 22.7), on lm_head (N = 8195 is
-    // not tileable: 12.1 vs 42.8 for the canonical kernel) and is the only tcgen05 path below 64 rows
+    // measured at M = 64 (profiles/batched_kernels_r02.json, us per call; tiled gemm_tc / weight-streaming with the K
+    // slices in a cluster / the same with L2 tickets): qkv 9.2 / 7.5 / 11.4, out_proj 7.3 / 6.1 / 15.7, fc1 9.4 / 8.1 /
+    // 11.6, fc2 22.7 / 8.2 / 18.8, lm_head - / 10.4 / 12.2 (N = 8195 is not tileable; canonical kernel 42.7).  So up to
+    // 128 rows the cluster kernel takes every matrix; the tiled kernel keeps the 257-row prefill passes.
     const bool tiled_ok = M >= 64 && linear_tc_supported(M, N, K, ldx, ldy, x, W, y);
-    if (tiled_ok && (K <= 1024 || M > 128))
-      return launch_linear_tc((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
-    if (M <= 128 && linear_ws_supported(M, N, K, ldx, x, W))
+    const bool ws_ok = M <= 128 && linear_ws_supported(M, N, K, ldx, x, W);
+    if (ws_ok && (linear_ws_mode() || !tiled_ok || K > 1024))
       return launch_linear_ws((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, ws.tc_scratch, st);
     if (tiled_ok) return launch_linear_tc((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
   }
@@ -122,9 +129,15 @@ static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, in
     __half* kc = kv_layer(kv, L, 0, B, T) + (size_t)slot0 * NHEAD * T * HD;
     __half* vc = kv_layer(kv, L, 1, B, T) + (size_t)slot0 * NHEAD * T * HD;
     if (dec_linear(tc, ws, w->wqkv[L], w->bqkv[L], ws.x16, HID, ws.qkv, QKV, M, QKV, HID, MA_EPI_NONE, st)) return 1;
-    if (launch_kv_append(ws.qkv, M, rows_per_slot, ws.nkeys, kc, vc, T, st)) return 1;
-    if (launch_attention(ws.qkv, QKV, kc, vc, T, NHEAD, rows_per_slot, nullptr, ws.nkeys, max_keys, M, 0.125f,
-                         ws.attn16, HID, scratch, st)) return 1;
+    if (rows_per_slot == 1 && !g_no_stream_attn) {
+      // decode step of a batch: persistent pipelined kernel, k / v of the current token appended on the way
+      if (launch_attention_decode(ws.qkv, QKV, kc, vc, T, ws.nkeys, max_keys, M, 0.125f, ws.attn16, HID, scratch, false,
+                                  st)) return 1;
+    } else {
+      if (launch_kv_append(ws.qkv, M, rows_per_slot, ws.nkeys, kc, vc, T, st)) return 1;
+      if (launch_attention(ws.qkv, QKV, kc, vc, T, NHEAD, rows_per_slot, nullptr, ws.nkeys, max_keys, M, 0.125f,
+                           ws.attn16, HID, scratch, st)) return 1;
+    }
     if (dec_linear(tc, ws, w->wo[L], w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID, MA_EPI_NONE, st)) return 1;
     if (launch_layernorm(ws.hres, ws.y16, w->ln1g[L], w->ln1b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
     if (dec_linear(tc, ws, w->w1[L], w->b1[L], ws.x16, HID, ws.f16, FFN, M, FFN, HID, MA_EPI_RELU, st)) return 1;
@@ -286,6 +299,7 @@ int ma_linear_f16(const void* W, const void* bias, const void* x, int ldx, void*
 }
 
 size_t ma_linear_ws_scratch_bytes(void) { return linear_ws_scratch_bytes(); }
+void ma_linear_ws_set_mode(int cluster) { linear_ws_set_mode(cluster); }
 
 int ma_linear_ws_f16(const void* W, const void* bias, const void* x, int ldx, void* y, int ldy, int M, int N, int K,
                      int epilogue, void* scratch, void* stream) {
@@ -310,6 +324,16 @@ int ma_attention_f16(const void* q, int ldq, const void* K, const void* V, long 
   }
   return launch_attention((const __half*)q, ldq, (const __half*)K, (const __half*)V, T, H, 1, slots, nkeys, max_keys, M,
                           scale, (__half*)out, ldo, scratch, (cudaStream_t)stream);
+}
+
+int ma_attention_decode_f16(const void* qkv, int ldq, void* K, void* V, long T, const int* nkeys, int max_keys, int M,
+                            float scale, void* out, int ldo, void* scratch, void* stream) {
+  if (!qkv || !K || !V || !nkeys || !out || !scratch || M < 1 || max_keys < 1 || max_keys > T || ldq < 3 * HID) {
+    set_error("ma_attention_decode_f16: bad arguments (M=%d, max_keys=%d, T=%ld, ldq=%d)", M, max_keys, T, ldq);
+    return 1;
+  }
+  return launch_attention_decode((const __half*)qkv, ldq, (__half*)K, (__half*)V, T, nkeys, max_keys, M, scale,
+                                 (__half*)out, ldo, scratch, false, (cudaStream_t)stream);
 }
 
 int ma_sample_tokens(const void* logits, int B, int vocab, const ma_sampling* sampling, int32_t* out_tokens,

@@ -5,9 +5,14 @@
 // of spending 18-27 TFLOP/s of fp32 FMAs on it (profiles/batched_kernels_r01.json: 76 us per layer at M = 64).
 //
 // The decoder's matrices have only 8..65 row blocks, far fewer than the 148 SMs, so the K dimension is split across
-// CTAs as well (grid = row blocks x K slices ~ one CTA per SM).  Every CTA leaves its fp32 partial tile in an
-// L2-resident scratch area; the LAST CTA of a row block (atomic ticket) adds the K slices in a fixed order -- the
-// result does not depend on which CTA finishes last -- and applies bias / activation / fp16 rounding.
+// CTAs as well (grid = row blocks x K slices ~ one CTA per SM).  Two ways to add the slices, both in slice order, so
+// the result never depends on timing:
+//   * cluster mode (default): the K slices of a row block are ONE thread-block cluster (2 / 4 / 8 CTAs).  Every CTA
+//     parks its fp32 tile in its own shared memory (the drained pipeline stages), the cluster synchronises, and CTA r
+//     finishes activation rows r, r + ks, ... by reading the ks tiles over distributed shared memory
+//     (ld.shared::cluster.v4) -- no round trip through L2, no tickets, no serialised last CTA;
+//   * ticket mode (MA_B200_WS_CLUSTER=0, ma_linear_ws_set_mode): fp32 partial tiles in an L2-resident scratch area and
+//     the LAST CTA of a row block (atomic ticket) adds them and applies bias / activation / fp16 rounding.
 //
 // Used by the batched decode step and (with gemm_tc_kernel for the 257-row prefill passes) wherever the decoder runs
 // with a logits TOLERANCE instead of bit-exact ids: sampling (BASELINE configs 3-5) or MA_GEN_TC.  The tensor core adds
@@ -17,6 +22,8 @@
 // CTA = 192 threads: warp 0 TMA producer (W tile [128 x 64], x tile [MP x 64] per stage, 6-8 stages), warp 1 MMA issuer
 // (4 x tcgen05.mma.cta_group::1.kind::f16 M128 N=MP K16 per stage, accumulator [128 lanes x MP columns] in TMEM),
 // warps 2-5 epilogue (tcgen05.ld 32x32b: a thread owns one weight row = one output column n of y).
+#include <stdlib.h>
+
 #include "internal.h"
 #include "tc_common.cuh"
 
@@ -36,6 +43,18 @@ struct alignas(1024) WsSmem {
   int last;
 };
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16 bytes from the shared memory of CTA `rank` of this cluster, at the same offset as `addr` in this CTA
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr, uint32_t rank) {
+  uint32_t ra;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ float gelu_erf_ws(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 __device__ __forceinline__ __half ws_epilogue(float v, const __half* bias, int n, int epi) {
@@ -53,7 +72,7 @@ template <int MP>
 __global__ void __launch_bounds__(WS_THREADS, 1)
     gemm_ws_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                    const __half* __restrict__ bias, __half* __restrict__ y, int ldy, int M, int N, int nkb_total, int epi,
-                   float* __restrict__ part, unsigned* __restrict__ tickets, int npad) {
+                   float* __restrict__ part, unsigned* __restrict__ tickets, int npad, int cluster) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   WsSmem<MP>& sm = *reinterpret_cast<WsSmem<MP>*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int TCOLS = MP < 32 ? 32 : MP;   // TMEM allocations are powers of two >= 32 columns
@@ -126,7 +145,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
     for (int c0 = 0; c0 < MP; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r);
-      if (n < N) {
+      if (cluster) {
+        // park the tile as red[m][128] in the drained pipeline stages (every MMA that read them has completed)
+        float* red = reinterpret_cast<float*>(sm.a);
+#pragma unroll
+        for (int j = 0; j < 32; j++) red[(c0 + j) * WS_BN + et] = __uint_as_float(r[j]);
+      } else if (n < N) {
 #pragma unroll
         for (int j = 0; j < 32; j++) {
           const int m = c0 + j;
@@ -138,7 +162,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       }
     }
     tc_fence_before();
-    if (ks > 1) {
+    if (ks > 1 && !cluster) {
       // last CTA of this row block adds the K slices in slice order (deterministic) and finishes the rows
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -182,6 +206,46 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
       }
     }
   }
+  if (cluster) {
+    // K slices of this row block = the CTAs of this cluster.  Barrier 1: every tile is parked; barrier 2: every CTA is
+    // done reading its peers' shared memory (no CTA may exit before that).
+    __syncwarp();
+    cluster_sync_all();
+    if (warp >= 2) {
+      uint32_t rank;
+      asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+      const int et = 32 * (warp & 3) + lane;
+      const int nq = 4 * (et & 31), mg = et >> 5;      // 32 column quads x 4 row groups
+      const uint32_t red0 = smem_u32(sm.a);
+      // CTA `rank` finishes activation rows rank, rank + ks, ...; its 4 row groups take every 4th of those
+      for (int m = (int)rank + ks * mg; m < M; m += 4 * ks) {
+        float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 pv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k < ks) pv[k] = ld_dsmem_f4(red0 + (uint32_t)((m * WS_BN + nq) * 4), (uint32_t)k);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k < ks) { acc.x += pv[k].x; acc.y += pv[k].y; acc.z += pv[k].z; acc.w += pv[k].w; }   // slice order
+        const float v4[4] = {acc.x, acc.y, acc.z, acc.w};
+        const int n = n0 + nq;
+        if (n + 3 < N && (ldy & 3) == 0) {
+          __half2 h01 = __halves2half2(ws_epilogue(v4[0], bias, n, epi), ws_epilogue(v4[1], bias, n + 1, epi));
+          __half2 h23 = __halves2half2(ws_epilogue(v4[2], bias, n + 2, epi), ws_epilogue(v4[3], bias, n + 3, epi));
+          uint2 u;
+          u.x = *reinterpret_cast<uint32_t*>(&h01);
+          u.y = *reinterpret_cast<uint32_t*>(&h23);
+          *reinterpret_cast<uint2*>(y + (long)m * ldy + n) = u;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if (n + i < N) y[(long)m * ldy + n + i] = ws_epilogue(v4[i], bias, n + i, epi);
+        }
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();
+  }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
@@ -199,17 +263,37 @@ bool linear_ws_supported(int M, int N, int K, int ldx, const void* x, const void
 
 template <int MP>
 static int launch_ws(const CUtensorMap& mw, const CUtensorMap& mx, const __half* bias, __half* y, int ldy, int M, int N,
-                     int nkb, int epi, float* part, unsigned* tickets, int npad, dim3 grid, cudaStream_t st) {
+                     int nkb, int epi, float* part, unsigned* tickets, int npad, dim3 grid, int cluster,
+                     cudaStream_t st) {
   const size_t smem = sizeof(WsSmem<MP>) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(gemm_ws_kernel<MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  gemm_ws_kernel<MP><<<grid, WS_THREADS, smem, st>>>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(WS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = grid.y;   // the K slices of a row block are one cluster
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cluster ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, gemm_ws_kernel<MP>, mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, cluster);
   count_launch();
   return check_launch("gemm_ws_kernel") ? 0 : 1;
 }
+
+static int g_ws_cluster = [] {
+  const char* e = getenv("MA_B200_WS_CLUSTER");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+void linear_ws_set_mode(int cluster) { g_ws_cluster = cluster ? 1 : 0; }
+int linear_ws_mode() { return g_ws_cluster; }
 
 // scratch: linear_ws_scratch_bytes() bytes, its last WS_TICKETS words zero on first use (they return to zero)
 int launch_linear_ws(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
@@ -221,13 +305,24 @@ int launch_linear_ws(const __half* W, const __half* bias, const __half* x, int l
   const int tiles = (N + WS_BN - 1) / WS_BN, nkb = K / WS_BK;
   const int npad = tiles * WS_BN;
   const size_t avail = linear_ws_scratch_bytes() - WS_TICKETS * sizeof(unsigned);
-  // K is split only for matrices with few row blocks (out_proj, fc2: 8): the last-CTA fix-up costs ~1 us per K slice,
-  // more than a deep pipeline gains on 16+ CTAs (B200, M = 64: profiles/batched_kernels_r02.json)
-  int ks = tiles >= 16 ? 1 : 148 / tiles;
-  if (ks > 4) ks = 4;
-  if (ks > nkb) ks = nkb;
-  if (ks < 1) ks = 1;
-  while (ks > 1 && (size_t)ks * M * npad * sizeof(float) > avail) ks--;
+  int ks, cluster = 0;
+  if (g_ws_cluster) {
+    // cluster mode: the largest cluster of 8 / 4 / 2 K slices that keeps the grid within one wave of the SMs that can
+    // host such clusters on a B200 (1 CTA per SM: 15 x 8, 33 x 4, 74 x 2 co-resident, profiles/microbench_cluster_r02)
+    ks = 1;
+    if (tiles * 8 <= 120 && nkb >= 16) ks = 8;          // out_proj, fc2: 8 row blocks -> 64 CTAs
+    else if (tiles * 4 <= 132 && nkb >= 8) ks = 4;      // qkv 24 -> 96, fc1 32 -> 128
+    else if (tiles * 2 <= 148 && nkb >= 4) ks = 2;      // lm_head 65 -> 130
+    cluster = ks > 1;
+  } else {
+    // ticket mode: K is split only for matrices with few row blocks (out_proj, fc2: 8): the last-CTA fix-up costs ~1 us
+    // per K slice, more than a deep pipeline gains on 16+ CTAs (B200, M = 64: profiles/batched_kernels_r02.json)
+    ks = tiles >= 16 ? 1 : 148 / tiles;
+    if (ks > 4) ks = 4;
+    if (ks > nkb) ks = nkb;
+    if (ks < 1) ks = 1;
+    while (ks > 1 && (size_t)ks * M * npad * sizeof(float) > avail) ks--;
+  }
   float* part = reinterpret_cast<float*>(scratch);
   unsigned* tickets = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + avail);
   const int MP = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
@@ -235,10 +330,10 @@ int launch_linear_ws(const __half* W, const __half* bias, const __half* x, int l
   if (tc_make_map(&mw, W, N, K, K, WS_BN, WS_BK) || tc_make_map(&mx, x, M, K, ldx, MP, WS_BK)) return 1;
   const dim3 grid(tiles, ks);
   switch (MP) {
-    case 16: return launch_ws<16>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, st);
-    case 32: return launch_ws<32>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, st);
-    case 64: return launch_ws<64>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, st);
-    default: return launch_ws<128>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, st);
+    case 16: return launch_ws<16>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, st);
+    case 32: return launch_ws<32>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, st);
+    case 64: return launch_ws<64>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, st);
+    default: return launch_ws<128>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, st);
   }
 }
 

@@ -49,12 +49,17 @@ int launch_linear_tc(const __half* W, const __half* bias, const __half* x, int l
 
 // gemm_ws.cu (tcgen05 weight-streaming GEMM for M <= 128 rows: batched decode steps under a tolerance)
 size_t linear_ws_scratch_bytes();
+void linear_ws_set_mode(int cluster);
+int linear_ws_mode();   // 1: K slices reduced over distributed shared memory (default), 0: L2 + tickets
 bool linear_ws_supported(int M, int N, int K, int ldx, const void* x, const void* W);
 int launch_linear_ws(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
                      int K, int epi, void* scratch, cudaStream_t st);
 
 // attention.cu
 size_t attention_scratch_bytes(int M, int H, int max_keys);
+// decode attention of M cache slots (one query row each) + append of the current k / v (attention_stream.cu)
+int launch_attention_decode(const __half* qkv, int ldq, __half* K, __half* V, long T, const int* nkeys, int max_keys,
+                            int M, float scale, __half* out, int ldo, void* scratch, bool pdl, cudaStream_t st);
 int launch_attention(const __half* q, int ldq, const __half* K, const __half* V, long T, int H, int rows_per_slot,
                      const int* slots, const int* nkeys, int max_keys, int M, float scale, __half* out, int ldo,
                      void* scratch, cudaStream_t st);

@@ -109,6 +109,45 @@ def test_attention_bit_exact(H, T, nk):
 
 
 @gpu
+@pytest.mark.parametrize("T,nk", [(300, [1, 2, 33, 256, 257, 258, 300]), (1100, [1100, 513, 1024, 1025, 7]),
+                                  (7500, [7459, 7425, 258, 4096] * 6)])
+def test_attention_decode_stream_bit_exact(T, nk):
+    """attention_stream_kernel (persistent, pipelined, kv append folded in) against the oracle's canonical attention:
+    every cache slot has its own length; the cache row of the current token is poisoned before the call and must hold
+    the k / v of the qkv buffer afterwards.  Chunk boundaries (256, 257, 1024, 1025), single-key rows, >= 29 chunks
+    (two merge rounds) and more (row, head, chunk) items than one wave of CTAs are all in the cases."""
+    from meshanything_b200 import capi
+    from oracle import decoder as orc
+    g = torch.Generator().manual_seed(T)
+    M, H = len(nk), 16
+    qkv = torch.randn(M, 3072, generator=g).half()
+    k = torch.randn(M, H, T, 64, generator=g).half()
+    v = torch.randn(M, H, T, 64, generator=g).half()
+    d = _dev()
+    kd, vd = k.clone(), v.clone()
+    for m, n in enumerate(nk):
+        kd[m, :, n - 1] = float("nan")
+        vd[m, :, n - 1] = float("nan")
+        k[m, :, n - 1] = qkv[m, 1024:2048].view(H, 64)
+        v[m, :, n - 1] = qkv[m, 2048:].view(H, 64)
+    kd, vd = kd.to(d), vd.to(d)
+    nkeys = torch.tensor(nk, dtype=torch.int32, device=d)
+    got = capi.attention_decode_f16(qkv.to(d), kd, vd, nkeys).cpu()
+    assert torch.equal(kd.cpu().view(torch.int16), k.view(torch.int16))
+    assert torch.equal(vd.cpu().view(torch.int16), v.view(torch.int16))
+    distinct = {}
+    for m, n in enumerate(nk):
+        if (n, m % 4) in distinct and M > 8:      # the long case repeats lengths: check each length on a few rows only
+            continue
+        distinct[(n, m % 4)] = 1
+        ref = orc.attention(qkv[m:m + 1, :1024].view(1, H, 64), k[m], v[m], [n])
+        assert torch.equal(got[m].view(torch.int16), ref.view(-1).view(torch.int16)), (m, n)
+    # a second launch on the same scratch (tickets re-armed) gives the same bits
+    again = capi.attention_decode_f16(qkv.to(d), kd, vd, nkeys).cpu()
+    assert torch.equal(again.view(torch.int16), got.view(torch.int16))
+
+
+@gpu
 @pytest.mark.parametrize("M,N,K,epi", [(128, 128, 256, 0), (257, 768, 768, 0), (4096, 1536, 768, 0), (130, 128, 256, 1),
                                         (1057, 3072, 768, 2), (300, 768, 3072, 0), (64, 1152, 768, 0)])
 def test_linear_tensor_core(M, N, K, epi):
@@ -139,11 +178,14 @@ def test_linear_tensor_core(M, N, K, epi):
 @pytest.mark.parametrize("M,N,K,epi", [(1, 1024, 1024, 0), (5, 3072, 1024, 0), (16, 1024, 4096, 0), (33, 4096, 1024, 1),
                                         (64, 1024, 1024, 0), (64, 8195, 1024, 0), (128, 4096, 1024, 1), (100, 768, 3072, 2),
                                         (2, 200, 64, 0)])
-def test_linear_weight_streaming_tensor_core(M, N, K, epi):
-    """gemm_ws_kernel (swap-AB tcgen05 GEMM for M <= 128 rows, K split across CTAs, deterministic last-CTA reduction):
-    fp16 in, fp32 accumulate in the hardware's order -> compared with an fp64 product rounded once to fp16 and with the
-    canonical kernel; two runs give identical bits (the K-slice sum does not depend on which CTA finishes last)."""
+@pytest.mark.parametrize("cluster", [1, 0])
+def test_linear_weight_streaming_tensor_core(M, N, K, epi, cluster):
+    """gemm_ws_kernel (swap-AB tcgen05 GEMM for M <= 128 rows, K split across CTAs): K slices added over distributed
+    shared memory inside a thread-block cluster (cluster = 1, the default) or through L2 with an atomic ticket
+    (cluster = 0).  fp16 in, fp32 accumulate in the hardware's order -> compared with an fp64 product rounded once to
+    fp16 and with the canonical kernel; two runs give identical bits (the K-slice sum is taken in slice order)."""
     from meshanything_b200 import capi
+    capi.lib().ma_linear_ws_set_mode(cluster)
     g = torch.Generator().manual_seed(M * 31 + N + K)
     w = (torch.randn(N, K, generator=g) * 0.05).half()
     b = (torch.randn(N, generator=g) * 0.1).half() if N != 8195 else None       # lm_head has no bias
@@ -165,6 +207,7 @@ def test_linear_weight_streaming_tensor_core(M, N, K, epi):
         diff = (got.float() - canon.float()).abs()
         assert (diff <= 2.0 ** -9 * canon.float().abs() + 1e-3).all()
         assert (diff == 0).float().mean() > 0.97
+    capi.lib().ma_linear_ws_set_mode(1)
 
 
 def _hf_support(row: torch.Tensor, top_k: int, top_p: float):

@@ -36,6 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--skip-attention", action="store_true")
+    ap.add_argument("--skip-linear", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     B, H, D = args.batch, 16, 64
@@ -57,13 +58,22 @@ def main():
                                           capi.stream_ptr()), "attn")
         us = timed(run)
         nbytes = 2 * B * H * nk * D * 2
+        qkv = torch.randn(B, 3072, device=dev, dtype=torch.float16)
+        o2 = torch.empty((B, 1024), dtype=torch.float16, device=dev)
+
+        def run_stream():     # attention_stream_kernel: persistent + pipelined, kv append folded in
+            capi.check(L.ma_attention_decode_f16(capi.ptr(qkv), 3072, capi.ptr(k), capi.ptr(v), T, capi.ptr(nkeys), nk, B,
+                                                 C.c_float(0.125), capi.ptr(o2), 1024, capi.ptr(scratch),
+                                                 capi.stream_ptr()), "attn stream")
+        us2 = timed(run_stream)
         out["attention"].append({"nkeys": nk, "us": round(us, 2), "kv_MB": round(nbytes / 1e6, 1),
-                                 "GBps": round(nbytes / us / 1e3, 1)})
+                                 "GBps": round(nbytes / us / 1e3, 1),
+                                 "stream": {"us": round(us2, 2), "GBps": round(nbytes / us2 / 1e3, 1)}})
         del k, v
 
     shapes = [("qkv", 3072, 1024), ("out_proj", 1024, 1024), ("fc1", 4096, 1024), ("fc2", 1024, 4096),
               ("lm_head", 8195, 1024)]
-    for name, N, K in shapes:
+    for name, N, K in (() if args.skip_linear else shapes):
         # 24 distinct weight matrices rotated so that weights come from HBM, as in the layer loop
         ws = [torch.randn(N, K, device=dev, dtype=torch.float16) * 0.02 for _ in range(24)]
         b = torch.zeros(N, device=dev, dtype=torch.float16)
@@ -78,7 +88,9 @@ def main():
                     f(w, b, x)
             return g
         rec = {"name": name, "N": N, "K": K}
-        for tag, f in (("canon", capi.linear_f16), ("tcgen05", capi.linear_tc_f16), ("tcgen05_ws", capi.linear_ws_f16)):
+        for tag, f in (("canon", capi.linear_f16), ("tcgen05", capi.linear_tc_f16), ("tcgen05_ws", capi.linear_ws_f16),
+                       ("tcgen05_ws_ticket", capi.linear_ws_f16)):
+            L.ma_linear_ws_set_mode(0 if tag == "tcgen05_ws_ticket" else 1)
             try:
                 g = graph_of(f)
                 us = timed(g.replay, n=10, warm=2) / 24
@@ -87,6 +99,7 @@ def main():
             except Exception as e:  # noqa: BLE001
                 rec[tag] = {"error": str(e)[:200]}
         out["linear"].append(rec)
+    L.ma_linear_ws_set_mode(1)
     print(json.dumps(out))
 
 
