@@ -37,13 +37,14 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--skip-attention", action="store_true")
     ap.add_argument("--skip-linear", action="store_true")
+    ap.add_argument("--only-keys", type=int, default=0, help="a single context length for the attention part")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     B, H, D = args.batch, 16, 64
     L = capi.lib()
     out = {"batch": B, "attention": [], "linear": []}
 
-    for nk in (() if args.skip_attention else (512, 2048, 4096, 7459)):
+    for nk in (() if args.skip_attention else ((args.only_keys,) if args.only_keys else (512, 2048, 4096, 7459))):
         T = nk
         k = torch.randn(B, H, T, D, device=dev, dtype=torch.float16)
         v = torch.randn(B, H, T, D, device=dev, dtype=torch.float16)

@@ -49,7 +49,8 @@ launches(f"gpurun_out/launches_{tag}.csv")
 full(f"gpurun_out/prof_mega_{tag}.ncu-rep", "Persistent decode kernel")
 full(f"gpurun_out/prof_gemm_tc_{tag}.ncu-rep", "tcgen05 + TMA GEMM of the encoder (batch 8: M = 2056 / 32768 rows)")
 full(f"gpurun_out/prof_attn_tc_{tag}.ncu-rep", "tcgen05 flash attention of the encoder (batch 8: cross-attention 257 x 4096 keys, self-attention 257 x 257)")
-full(f"gpurun_out/prof_gemm_ws_{tag}.ncu-rep", "Weight-streaming tcgen05 GEMM of the batched decode step (M = 64)")
+full(f"gpurun_out/prof_gemm_ws_{tag}.ncu-rep", "Weight-streaming tcgen05 GEMM of the batched decode step (M = 64; K slices = one thread-block cluster)")
+full(f"gpurun_out/prof_attn_stream_{tag}.ncu-rep", "Persistent pipelined decode attention of a batch (batch 64, 7459 / 4096 keys)")
 full(f"gpurun_out/prof_batched_{tag}.ncu-rep", "Canonical CUDA-core GEMM and attention kernels (batch 8 decode / prefill)")
 def traffic(path, tokens):
     if not os.path.exists(path):
