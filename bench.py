@@ -162,8 +162,8 @@ def batched_decode_steps(arena, n_layers, B, F, sampling, contexts, steps=200, w
     return {"batch_per_gpu": B, "faces": F, "sampling": bool(sampling), "kv_cache_GB": kv_bytes / 1e9,
             "steps_timed_per_context": steps, "contexts": rows, "tokens_per_s_over_contexts": tps,
             "peak_GBps": peak, "peak_source": peak_src,
-            "kernels": "gemm_ws_kernel (tcgen05, swap-AB, split-K) + attention_kernel + sample_kernel in one CUDA graph per step"
-                       if sampling else "gemm_canon_kernel + attention_kernel + sample_kernel in one CUDA graph per step",
+            "kernels": "gemm_ws_kernel (tcgen05, swap-AB, K slices in a cluster) + attention_stream_kernel + sample_kernel in one CUDA graph per step"
+                       if sampling else "gemm_canon_kernel + attention_stream_kernel + sample_kernel in one CUDA graph per step",
             "note": "decode steps only (no encoder / prefill / detokenizer); KV zero-filled, state set by ma_decode_slots_seek"}
 
 
@@ -361,7 +361,7 @@ def main():
         "kernel": ("decode_mega_kernel (persistent: all 121 phases of a token, 512 tokens per launch)"
                    if (B == 1 and not args.sampling and not (flags & capi.GEN_NO_MEGA)) else
                    "decode step = 97 fast_gemv_kernel + 24 attention_kernel launches (one CUDA graph)" if B == 1 else
-                   "decode step: gemm_ws_kernel (tcgen05 swap-AB split-K) + attention_kernel + sample_kernel, one CUDA graph"
+                   "decode step: gemm_ws_kernel (tcgen05 swap-AB, K slices in a cluster) + attention_stream_kernel + sample_kernel, one CUDA graph"
                    if args.sampling else "decode step (gemm_canon + attention kernels, one CUDA graph)"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
         "traffic": traffic,

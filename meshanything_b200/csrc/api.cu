@@ -103,11 +103,16 @@ static const bool g_no_stream_attn = [] {
   return e && e[0] == '1';
 }();
 
+static const bool g_no_pdl = [] {   // MA_B200_NO_PDL=1: plain stream order between the kernels of a batched decode step
+  const char* e = getenv("MA_B200_NO_PDL");
+  return e && e[0] == '1';
+}();
+
 // One pass of the 24 layers over M rows (general batched kernels).
 // y = act(x W^T + b) for M rows of the decoder: the canonical kernel, or (tc) the tensor cores -- the weight-streaming
 // tcgen05 GEMM for M <= 128 rows (decode steps), the tiled tcgen05 GEMM for the 257-row prefill passes
 static int dec_linear(bool tc, const DecWs& ws, const void* W, const void* b, const __half* x, int ldx, __half* y, int ldy,
-                      int M, int N, int K, int epi, cudaStream_t st) {
+                      int M, int N, int K, int epi, cudaStream_t st, bool pdl = false) {
   if (tc) {
     // measured at M = 64 (profiles/batched_kernels_r02.json, us per call; tiled gemm_tc / weight-streaming with the K
     // slices in a cluster / the same with L2 tickets): qkv 9.2 / 7.5 / 11.4, out_proj 7.3 / 6.1 / 15.7, fc1 9.4 / 8.1 /
@@ -116,7 +121,7 @@ static int dec_linear(bool tc, const DecWs& ws, const void* W, const void* b, co
     const bool tiled_ok = M >= 64 && linear_tc_supported(M, N, K, ldx, ldy, x, W, y);
     const bool ws_ok = M <= 128 && linear_ws_supported(M, N, K, ldx, x, W);
     if (ws_ok && (linear_ws_mode() || !tiled_ok || K > 1024))
-      return launch_linear_ws((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, ws.tc_scratch, st);
+      return launch_linear_ws((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, ws.tc_scratch, st, pdl);
     if (tiled_ok) return launch_linear_tc((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
   }
   return launch_linear((const __half*)W, (const __half*)b, x, ldx, y, ldy, M, N, K, epi, st);
@@ -125,24 +130,28 @@ static int dec_linear(bool tc, const DecWs& ws, const void* W, const void* b, co
 static int run_layers(const ma_decoder_weights* w, const DecWs& ws, void* kv, int B, long T, int M, int rows_per_slot,
                       int slot0, int max_keys, cudaStream_t st, bool tc = false) {
   void* scratch = rows_per_slot > 1 ? ws.attn_scratch_pre : ws.attn_scratch;
+  // Decode step of a batch on the tensor-core path: the kernels of a layer are programmatic dependents of each other --
+  // a GEMM sends its first ring of WEIGHT tiles, the attention its first K / V rows, before the previous kernel has
+  // finished (each waits with griddepcontrol.wait before it touches anything the previous kernel wrote)
+  const bool pdl = tc && rows_per_slot == 1 && !g_no_pdl;
   for (int L = 0; L < w->n_layers; L++) {
     __half* kc = kv_layer(kv, L, 0, B, T) + (size_t)slot0 * NHEAD * T * HD;
     __half* vc = kv_layer(kv, L, 1, B, T) + (size_t)slot0 * NHEAD * T * HD;
-    if (dec_linear(tc, ws, w->wqkv[L], w->bqkv[L], ws.x16, HID, ws.qkv, QKV, M, QKV, HID, MA_EPI_NONE, st)) return 1;
+    if (dec_linear(tc, ws, w->wqkv[L], w->bqkv[L], ws.x16, HID, ws.qkv, QKV, M, QKV, HID, MA_EPI_NONE, st, pdl)) return 1;
     if (rows_per_slot == 1 && !g_no_stream_attn) {
       // decode step of a batch: persistent pipelined kernel, k / v of the current token appended on the way
-      if (launch_attention_decode(ws.qkv, QKV, kc, vc, T, ws.nkeys, max_keys, M, 0.125f, ws.attn16, HID, scratch, false,
+      if (launch_attention_decode(ws.qkv, QKV, kc, vc, T, ws.nkeys, max_keys, M, 0.125f, ws.attn16, HID, scratch, pdl,
                                   st)) return 1;
     } else {
       if (launch_kv_append(ws.qkv, M, rows_per_slot, ws.nkeys, kc, vc, T, st)) return 1;
       if (launch_attention(ws.qkv, QKV, kc, vc, T, NHEAD, rows_per_slot, nullptr, ws.nkeys, max_keys, M, 0.125f,
                            ws.attn16, HID, scratch, st)) return 1;
     }
-    if (dec_linear(tc, ws, w->wo[L], w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID, MA_EPI_NONE, st)) return 1;
-    if (launch_layernorm(ws.hres, ws.y16, w->ln1g[L], w->ln1b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
-    if (dec_linear(tc, ws, w->w1[L], w->b1[L], ws.x16, HID, ws.f16, FFN, M, FFN, HID, MA_EPI_RELU, st)) return 1;
-    if (dec_linear(tc, ws, w->w2[L], w->b2[L], ws.f16, FFN, ws.y16, HID, M, HID, FFN, MA_EPI_NONE, st)) return 1;
-    if (launch_layernorm(ws.hres, ws.y16, w->ln2g[L], w->ln2b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st)) return 1;
+    if (dec_linear(tc, ws, w->wo[L], w->bo[L], ws.attn16, HID, ws.y16, HID, M, HID, HID, MA_EPI_NONE, st, pdl)) return 1;
+    if (launch_layernorm(ws.hres, ws.y16, w->ln1g[L], w->ln1b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st, pdl)) return 1;
+    if (dec_linear(tc, ws, w->w1[L], w->b1[L], ws.x16, HID, ws.f16, FFN, M, FFN, HID, MA_EPI_RELU, st, pdl)) return 1;
+    if (dec_linear(tc, ws, w->w2[L], w->b2[L], ws.f16, FFN, ws.y16, HID, M, HID, FFN, MA_EPI_NONE, st, pdl)) return 1;
+    if (launch_layernorm(ws.hres, ws.y16, w->ln2g[L], w->ln2b[L], MA_LN_EPS, M, HID, ws.hres, ws.x16, st, pdl)) return 1;
   }
   return 0;
 }
@@ -196,7 +205,8 @@ static int enqueue_batched_step(const ma_decoder_weights* w, const DecWs& ws, vo
                                 const SampleArgs& sa, cudaStream_t s, bool tc) {
   if (launch_embed_tokens(w, ws.s, B, ws.hres, ws.x16, ws.nkeys, s)) return 1;
   if (run_layers(w, ws, kv, B, T, B, 1, 0, max_keys, s, tc)) return 1;
-  if (dec_linear(tc, ws, w->lm_head, nullptr, ws.x16, HID, ws.logits, w->vocab, B, w->vocab, HID, MA_EPI_NONE, s)) return 1;
+  if (dec_linear(tc, ws, w->lm_head, nullptr, ws.x16, HID, ws.logits, w->vocab, B, w->vocab, HID, MA_EPI_NONE, s,
+                 tc && !g_no_pdl)) return 1;
   return launch_sample(sa, s);
 }
 

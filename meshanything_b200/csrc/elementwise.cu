@@ -12,6 +12,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const __half* __re
   __shared__ float red[8];
   const long row = blockIdx.x;
   const int t = threadIdx.x;
+  pdl_trigger();   // the next kernel (a GEMM: weight tiles first) may start its prologue now
+  pdl_wait();      // no-op unless launched as a programmatic dependent; x / res16 come from the previous kernel
   float v[4];
   if (x) {
     const float4 xv = *reinterpret_cast<const float4*>(x + row * W + 4 * t);
@@ -41,13 +43,22 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const __half* __re
 }
 
 int launch_layernorm(const float* x, const __half* res16, const float* gamma, const float* beta, float eps, int M,
-                     int W, float* out32, __half* out16, cudaStream_t st) {
+                     int W, float* out32, __half* out16, cudaStream_t st, bool pdl) {
   if (M <= 0) return 0;
   if (W % 128 != 0 || W > 1024 || (!x && !res16)) {
     set_error("ma_layernorm: unsupported width %d or no input", W);
     return 1;
   }
-  layernorm_kernel<<<M, W / 4, 0, st>>>(x, res16, gamma, beta, eps, W, out32, out16);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(M);
+  cfg.blockDim = dim3(W / 4);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, layernorm_kernel, x, res16, gamma, beta, eps, W, out32, out16);
   count_launch();
   return check_launch("layernorm_kernel") ? 0 : 1;
 }

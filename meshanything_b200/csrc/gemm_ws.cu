@@ -105,16 +105,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
+  pdl_trigger();   // the next kernel may start its prologue (and, if it is a GEMM, its own weight tiles)
   if (warp == 0) {
-    // ---------------- TMA producer: this CTA's K slice of the weight row block (+ the matching columns of x)
+    // ---------------- TMA producer: this CTA's K slice of the weight row block (+ the matching columns of x).
+    // The weights do not depend on the previous kernel: the first ring of weight tiles goes out BEFORE the grid
+    // dependency resolves (programmatic dependent launch), the activation tiles after it.
     if (elect_one()) {
-      for (int i = 0; i < nk; i++) {
+      const int first = min(nk, WS_STAGES);
+      for (int i = 0; i < first; i++) {
+        mbar_expect_tx(&sm.full[i], STAGE_BYTES);
+        tma_load_2d(sm.a[i], &map_w, (kb0 + i) * WS_BK, n0, &sm.full[i]);   // rows beyond N are zero-filled
+      }
+      pdl_wait();
+      for (int i = 0; i < first; i++)
+        tma_load_2d(sm.b[i], &map_x, (kb0 + i) * WS_BK, 0, &sm.full[i]);    // rows beyond M are zero-filled
+      for (int i = first; i < nk; i++) {
         const int s = i % WS_STAGES;
         const uint32_t ph = (i / WS_STAGES) & 1;
         mbar_wait(&sm.empty[s], ph ^ 1);
         mbar_expect_tx(&sm.full[s], STAGE_BYTES);
-        tma_load_2d(sm.a[s], &map_w, (kb0 + i) * WS_BK, n0, &sm.full[s]);   // rows beyond N are zero-filled
-        tma_load_2d(sm.b[s], &map_x, (kb0 + i) * WS_BK, 0, &sm.full[s]);    // rows beyond M are zero-filled
+        tma_load_2d(sm.a[s], &map_w, (kb0 + i) * WS_BK, n0, &sm.full[s]);
+        tma_load_2d(sm.b[s], &map_x, (kb0 + i) * WS_BK, 0, &sm.full[s]);
       }
     }
   } else if (warp == 1) {
@@ -263,7 +274,7 @@ bool linear_ws_supported(int M, int N, int K, int ldx, const void* x, const void
 
 template <int MP>
 static int launch_ws(const CUtensorMap& mw, const CUtensorMap& mx, const __half* bias, __half* y, int ldy, int M, int N,
-                     int nkb, int epi, float* part, unsigned* tickets, int npad, dim3 grid, int cluster,
+                     int nkb, int epi, float* part, unsigned* tickets, int npad, dim3 grid, int cluster, bool pdl,
                      cudaStream_t st) {
   const size_t smem = sizeof(WsSmem<MP>) + 1024;
   static bool attr_done = false;
@@ -276,13 +287,22 @@ static int launch_ws(const CUtensorMap& mw, const CUtensorMap& mx, const __half*
   cfg.blockDim = dim3(WS_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 1;
-  at[0].val.clusterDim.y = grid.y;   // the K slices of a row block are one cluster
-  at[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (cluster) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 1;
+    at[na].val.clusterDim.y = grid.y;   // the K slices of a row block are one cluster
+    at[na].val.clusterDim.z = 1;
+    na++;
+  }
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    na++;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = cluster ? 1 : 0;
+  cfg.numAttrs = na;
   cudaLaunchKernelEx(&cfg, gemm_ws_kernel<MP>, mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, cluster);
   count_launch();
   return check_launch("gemm_ws_kernel") ? 0 : 1;
@@ -297,7 +317,7 @@ int linear_ws_mode() { return g_ws_cluster; }
 
 // scratch: linear_ws_scratch_bytes() bytes, its last WS_TICKETS words zero on first use (they return to zero)
 int launch_linear_ws(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
-                     int K, int epi, void* scratch, cudaStream_t st) {
+                     int K, int epi, void* scratch, cudaStream_t st, bool pdl) {
   if (!linear_ws_supported(M, N, K, ldx, x, W)) {
     set_error("ma_linear_ws_f16: unsupported shape M=%d N=%d K=%d ldx=%d", M, N, K, ldx);
     return 1;
@@ -330,10 +350,10 @@ int launch_linear_ws(const __half* W, const __half* bias, const __half* x, int l
   if (tc_make_map(&mw, W, N, K, K, WS_BN, WS_BK) || tc_make_map(&mx, x, M, K, ldx, MP, WS_BK)) return 1;
   const dim3 grid(tiles, ks);
   switch (MP) {
-    case 16: return launch_ws<16>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, st);
-    case 32: return launch_ws<32>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, st);
-    case 64: return launch_ws<64>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, st);
-    default: return launch_ws<128>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, st);
+    case 16: return launch_ws<16>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, pdl, st);
+    case 32: return launch_ws<32>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, pdl, st);
+    case 64: return launch_ws<64>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, pdl, st);
+    default: return launch_ws<128>(mw, mx, bias, y, ldy, M, N, nkb, epi, part, tickets, npad, grid, cluster, pdl, st);
   }
 }
 

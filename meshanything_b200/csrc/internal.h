@@ -53,7 +53,7 @@ void linear_ws_set_mode(int cluster);
 int linear_ws_mode();   // 1: K slices reduced over distributed shared memory (default), 0: L2 + tickets
 bool linear_ws_supported(int M, int N, int K, int ldx, const void* x, const void* W);
 int launch_linear_ws(const __half* W, const __half* bias, const __half* x, int ldx, __half* y, int ldy, int M, int N,
-                     int K, int epi, void* scratch, cudaStream_t st);
+                     int K, int epi, void* scratch, cudaStream_t st, bool pdl = false);
 
 // attention.cu
 size_t attention_scratch_bytes(int M, int H, int max_keys);
@@ -66,7 +66,7 @@ int launch_attention(const __half* q, int ldq, const __half* K, const __half* V,
 
 // elementwise.cu
 int launch_layernorm(const float* x, const __half* res16, const float* gamma, const float* beta, float eps, int M,
-                     int W, float* out32, __half* out16, cudaStream_t st);
+                     int W, float* out32, __half* out16, cudaStream_t st, bool pdl = false);
 int launch_embed_prefix(const ma_decoder_weights* w, const float* prefix, int B, float* hres, __half* x16, int* nkeys,
                         cudaStream_t st);
 int launch_embed_tokens(const ma_decoder_weights* w, SeqState s, int B, float* hres, __half* x16, int* nkeys,
