@@ -98,8 +98,35 @@ if os.path.exists(bj) and os.path.getsize(bj) > 0:
           f"| CPU baseline (oracle, {d['cpu_baseline']['cores'] if d.get('cpu_baseline') else '?'} cores) | {d['cpu_baseline']['value'] if d.get('cpu_baseline') else float('nan'):.1f} tokens/s |",
           f"| kernels launched in the timed region | {d['gpu_launches']} |",
           "",
-          "Files: `ncu_summary_%s.md` (launch list + full-capture metrics), `microbench_%s.txt` (hand-off / GEMV micro-benchmarks), "
-          "`mega_trace_%s.txt` (phase timeline of the persistent kernel from its own globaltimer stamps: short and long context).\n" % (tag, tag, tag)]
+          ""]
+    def other(fn, label):
+        path = f"profiles/{fn}"
+        if not os.path.exists(path):
+            return
+        o = json.load(open(path))
+        rr = o["roofline"]
+        md.append(f"| {label} (`{fn}`) | {o['value']:.0f} tokens/s (e2e {o['e2e']['value']:.0f}), {o['ms_per_step'] / 1e3:.1f} s per step of "
+                  f"{o['config']['global_batch']} meshes on {o['n_gpus']} GPU(s), {rr['us_per_step_avg'] / 1e3:.2f} ms per decode step, "
+                  f"{rr['frac']:.3f} of the HBM roofline |")
+    md += ["## Other BASELINE configurations (full runs, `bench.py --config N --lean`)\n", "| run | result |\n|---|---|"]
+    other(f"bench_{tag}_cfg3.json", "config 3: batch 64, F = 800, top-k / top-p")
+    other(f"bench_{tag}_cfg3_before_stream_attention.json", "config 3 before attention_stream_kernel / cluster GEMM / PDL")
+    other(f"bench_{tag}_cfg4_n8.json", "config 4: 512 shapes on 8 GPUs (64 per GPU)")
+    other(f"bench_{tag}_cfg5.json", "config 5: batch 32 per GPU, F = 1600 (before attention_stream_kernel / cluster GEMM / PDL)")
+    md += ["",
+           "Bounded decode-step measurements of configs 3 and 5 at three contexts each are in the `extra` block of `bench_%s.json`." % tag,
+           "",
+           "## Files\n",
+           "* `ncu_summary_%s.md` — launch list of a bench run + `ncu --set full` metrics of `decode_mega_kernel`, `gemm_tc_kernel`, "
+           "`attention_tc_kernel`, `gemm_ws_kernel` (cluster split-K), `attention_stream_kernel`; `traffic_%s.json` = DRAM bytes per token of the "
+           "persistent kernel from that capture." % (tag, tag),
+           "* `batched_kernels_%s.json` — per-kernel A/B timings of the batched decode step (attention old / streaming at batch 8, 32, 64; every "
+           "decoder GEMM on the canonical, tiled tcgen05 and weight-streaming tcgen05 kernels with both K-slice reductions)." % tag,
+           "* `microbench_cluster_%s.txt` — cluster co-residency, DSMEM and flagged-word exchange micro-benchmarks behind DESIGN 4.1.2." % tag,
+           "* `mega_trace_%s*.txt` — phase timelines of the persistent kernel from its own globaltimer stamps (the row-split kernel that ships "
+           "and the abandoned column-split design)." % tag,
+           "* `sass_histogram_%s.md` — SASS mnemonics per kernel (UTCHMMA / UTMALDG / FHFMA / SYNCS evidence)." % tag,
+           ""]
     open("profiles/README.md", "w").write("\n".join(md))
     print("\n".join(md))
 if os.path.exists(f"gpurun_out/mega_trace_{tag}.txt"):
