@@ -5,7 +5,7 @@ import collections, csv, json, os, re, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 out = []
 
-def launches(path):
+def launches(path, title=None, keep=None):
     if not os.path.exists(path):
         return
     lines = [l for l in open(path) if not l.startswith("==")]
@@ -15,9 +15,11 @@ def launches(path):
         u = row["Metric Unit"]
         v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v * 1e6 if u == "s" else v
         name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("void ", "")
+        if keep and not keep(name, row["Grid Size"]):
+            continue
         agg[name + " grid=" + row["Grid Size"]].append(v)
     tot = sum(sum(v) for v in agg.values())
-    out.append(f"## Launch list ({os.path.basename(path)}; `ncu --metrics gpu__time_duration.sum --clock-control none`, cold cache, serialised)\n")
+    out.append(f"## {title or 'Launch list'} ({os.path.basename(path)}; `ncu --metrics gpu__time_duration.sum --clock-control none`, cold cache, serialised)\n")
     out.append("| kernel | launches | avg us | share |\n|---|---:|---:|---:|")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         out.append(f"| `{k}` | {len(v)} | {sum(v)/len(v):.2f} | {100*sum(v)/tot:.1f} % |")
@@ -46,6 +48,10 @@ def full(path, title):
         out.append("")
 
 launches(f"gpurun_out/launches_{tag}.csv")
+# the batched decode step of config 3 (batch 64, sampling): only the kernels of the per-step graph (64-row launches)
+launches(f"gpurun_out/launches_{tag}_cfg3.csv", "Launch list of the batched decode step (bench.py --config 3 --faces 16: contexts 258..402)",
+         keep=lambda n, g: any(k in n for k in ("gemm_ws_kernel", "attention_stream_kernel", "sample_kernel", "embed_tokens", "set_flag"))
+         or ("layernorm_kernel" in n and g.replace(" ", "").startswith("(64,")))
 full(f"gpurun_out/prof_mega_{tag}.ncu-rep", "Persistent decode kernel")
 full(f"gpurun_out/prof_gemm_tc_{tag}.ncu-rep", "tcgen05 + TMA GEMM of the encoder (batch 8: M = 2056 / 32768 rows)")
 full(f"gpurun_out/prof_attn_tc_{tag}.ncu-rep", "tcgen05 flash attention of the encoder (batch 8: cross-attention 257 x 4096 keys, self-attention 257 x 257)")
