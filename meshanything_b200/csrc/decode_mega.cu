@@ -22,8 +22,6 @@
 // width.  What round 2 keeps: the mixed-precision FMA (FHFMA) in every dot product, the
 // lane-transposed attention scores, the merge by every CTA at short contexts (one hand-off less), bounded waits that
 // surface as an error (lens = -1) instead of a silently wrong mesh, and the post-mortem record of the first time-out.
-#include <stdlib.h>
-
 #include "canon.cuh"
 #include "internal.h"
 
@@ -104,61 +102,22 @@ __device__ __forceinline__ bool poll_giveup(int* err, unsigned& spins) {
   }
   return false;
 }
-// Staggered polling.  A poll is an L2 round trip; with one poll in flight per word, a word that lands just after the
-// poll passed is seen a whole round trip later, and a gather needs ALL its words.  With c_poll_gap > 0 every wait keeps
-// a SECOND poll of the same word in flight, issued c_poll_gap cycles (about half a round trip) after the first, so a
-// new value is observed at most half a round trip late.  0 = one poll in flight (round-1 behaviour).
-constexpr int MG_POLL_GAP_DEFAULT = 0;
-__constant__ unsigned c_poll_gap = 0;
-__device__ __forceinline__ void poll_delay(unsigned cyc) {
-  unsigned t0, t;
-  asm volatile("mov.u32 %0, %%clock;" : "=r"(t0));
-  do {
-    asm volatile("mov.u32 %0, %%clock;" : "=r"(t));
-  } while (t - t0 < cyc);
-}
 // spin until both words carry epoch `ep`; returns the two data halves
 __device__ __forceinline__ uint2 ll_wait2(const uint2* p, uint32_t ep, int* err) {
   uint4 v = ll_load2(p);
   unsigned spins = 0;
-  const unsigned gap = c_poll_gap;
-  if (gap == 0) {
-    while (v.y != ep || v.w != ep) {
-      if (poll_giveup(err, spins)) break;
-      v = ll_load2(p);
-    }
-    return make_uint2(v.x, v.z);
-  }
-  poll_delay(gap);
-  uint4 w = ll_load2(p);
-  for (;;) {
-    if (v.y == ep && v.w == ep) break;
-    v = ll_load2(p);
-    if (w.y == ep && w.w == ep) { v = w; break; }
-    w = ll_load2(p);
+  while (v.y != ep || v.w != ep) {
     if (poll_giveup(err, spins)) break;
+    v = ll_load2(p);
   }
   return make_uint2(v.x, v.z);
 }
 __device__ __forceinline__ uint32_t ll_wait1(const uint2* p, uint32_t ep, int* err) {
   uint2 v = ll_load1(p);
   unsigned spins = 0;
-  const unsigned gap = c_poll_gap;
-  if (gap == 0) {
-    while (v.y != ep) {
-      if (poll_giveup(err, spins)) break;
-      v = ll_load1(p);
-    }
-    return v.x;
-  }
-  poll_delay(gap);
-  uint2 w = ll_load1(p);
-  for (;;) {
-    if (v.y == ep) break;
-    v = ll_load1(p);
-    if (w.y == ep) { v = w; break; }
-    w = ll_load1(p);
+  while (v.y != ep) {
     if (poll_giveup(err, spins)) break;
+    v = ll_load1(p);
   }
   return v.x;
 }
@@ -170,50 +129,17 @@ __device__ __forceinline__ void ll_wait_units(const uint2* p, int stride, uint32
 #pragma unroll
   for (int i = 0; i < N; i++) v[i] = ll_load2(p + 2 * i * stride);
   unsigned spins = 0;
-  const unsigned gap = c_poll_gap;
-  if (gap == 0) {
-    for (;;) {
-      bool ok = true;
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        if (v[i].y != ep || v[i].w != ep) {
-          ok = false;
-          v[i] = ll_load2(p + 2 * i * stride);
-        }
-      }
-      if (ok) break;
-      if (poll_giveup(err, spins)) break;
-    }
-  } else {
-    uint4 w[N];
-    bool have[N];
-    poll_delay(gap);
+  for (;;) {
+    bool ok = true;
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      w[i] = ll_load2(p + 2 * i * stride);
-      have[i] = false;
-    }
-    for (;;) {
-      bool ok = true;
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        if (!have[i]) {
-          if (v[i].y == ep && v[i].w == ep) have[i] = true;
-          else { ok = false; v[i] = ll_load2(p + 2 * i * stride); }
-        }
+      if (v[i].y != ep || v[i].w != ep) {
+        ok = false;
+        v[i] = ll_load2(p + 2 * i * stride);
       }
-      if (ok) break;
-      ok = true;
-#pragma unroll
-      for (int i = 0; i < N; i++) {
-        if (!have[i]) {
-          if (w[i].y == ep && w[i].w == ep) { v[i] = w[i]; have[i] = true; }
-          else { ok = false; w[i] = ll_load2(p + 2 * i * stride); }
-        }
-      }
-      if (ok) break;
-      if (poll_giveup(err, spins)) break;
     }
+    if (ok) break;
+    if (poll_giveup(err, spins)) break;
   }
 #pragma unroll
   for (int i = 0; i < N; i++) out[i] = make_uint2(v[i].x, v[i].z);
@@ -1039,10 +965,8 @@ __global__ void mega_pack_bias_kernel(MegaWs* ws, int rq, int ro, int r1, int r2
   ws->bias_cta[((size_t)L * 160 + cta) * 128 + t] = v;
 }
 
-static void mega_apply_poll_gap();
 int mega_prepare(const ma_decoder_weights* w, void* mega_ws, cudaStream_t st) {
   MegaWs* ws = reinterpret_cast<MegaWs*>(mega_ws);
-  mega_apply_poll_gap();
   if (cudaMemsetAsync(ws, 0, offsetof(MegaWs, bias_cta), st) != cudaSuccess) return 1;  // all epochs 0
   if (cudaMemcpyAsync(&ws->w, w, sizeof(ma_decoder_weights), cudaMemcpyHostToDevice, st) != cudaSuccess) return 1;
   const int rq = mega_rpc(QKV), ro = mega_rpc(HID), r1 = mega_rpc(FFN), r2 = mega_rpc(HID);
@@ -1053,17 +977,6 @@ int mega_prepare(const ma_decoder_weights* w, void* mega_ws, cudaStream_t st) {
   mega_pack_bias_kernel<<<dim3(160, w->n_layers), 128, 0, st>>>(ws, rq, ro, r1, r2);
   count_launch();
   return check_launch("mega_pack_bias_kernel") ? 0 : 1;
-}
-
-// cycles between the two polls a wait keeps in flight (0 = a single poll); MA_B200_MEGA_POLL_GAP overrides
-static int g_poll_gap = -1;
-static void mega_apply_poll_gap() {
-  if (g_poll_gap >= 0) return;
-  const char* e = getenv("MA_B200_MEGA_POLL_GAP");
-  g_poll_gap = e ? atoi(e) : MG_POLL_GAP_DEFAULT;
-  if (g_poll_gap < 0) g_poll_gap = 0;
-  const unsigned v = (unsigned)g_poll_gap;
-  cudaMemcpyToSymbol(c_poll_gap, &v, sizeof(v));
 }
 
 static int g_mega_fault = 0;

@@ -47,6 +47,22 @@ def test_dataset_normalisation(tmp_path, monkeypatch):
     assert s.shape == (2, 4096, 6) and s.dtype.is_floating_point
 
 
+def test_dataset_matches_reference_dataset_on_mouse_example(tmp_path, monkeypatch):
+    """BASELINE configs[0], host side: `Dataset('pc_normal', [mouse.npy])` under numpy seed 0 must hand the model exactly
+    the array the reference's own Dataset class (main.py:15-58) produced from the same file -- fixture
+    tests/golden/config1_mouse.npz, made by tests/golden/make_golden_inputs.py from the reference's class source."""
+    monkeypatch.syspath_prepend(ROOT)
+    import main as cli
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "config1_mouse.npz"))
+    path = tmp_path / "mouse.npy"
+    np.save(path, fx["raw"])
+    np.random.seed(0)                       # what set_seed(args.seed) leaves in numpy (main.py:97)
+    item = cli.Dataset("pc_normal", [str(path)])[0]
+    assert item["uid"] == "mouse"
+    assert item["pc_normal"].dtype == np.float16 and item["pc_normal"].shape == (4096, 6)
+    assert np.array_equal(item["pc_normal"].view(np.uint16), fx["pc_normal"].view(np.uint16))
+
+
 def test_obj_export_merges_vertices_and_faces(tmp_path, monkeypatch):
     monkeypatch.syspath_prepend(ROOT)
     import importlib

@@ -118,7 +118,8 @@ if os.path.exists(bj) and os.path.getsize(bj) > 0:
     other(f"bench_{tag}_cfg3.json", "config 3: batch 64, F = 800, top-k / top-p")
     other(f"bench_{tag}_cfg3_before_stream_attention.json", "config 3 before attention_stream_kernel / cluster GEMM / PDL")
     other(f"bench_{tag}_cfg4_n8.json", "config 4: 512 shapes on 8 GPUs (64 per GPU)")
-    other(f"bench_{tag}_cfg5.json", "config 5: batch 32 per GPU, F = 1600 (before attention_stream_kernel / cluster GEMM / PDL)")
+    other(f"bench_{tag}_cfg5.json", "config 5: batch 32 per GPU, F = 1600")
+    other(f"bench_{tag}_cfg5_before_stream_attention.json", "config 5 before attention_stream_kernel / cluster GEMM / PDL")
     md += ["",
            "Bounded decode-step measurements of configs 3 and 5 at three contexts each are in the `extra` block of `bench_%s.json`." % tag,
            "",
