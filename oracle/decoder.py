@@ -49,6 +49,9 @@ def lib():
         L.orc_attention.argtypes = [u16p, u16p, u16p, i32p, C.c_int, C.c_int, C.c_long, u16p]
         L.orc_exp.argtypes = [C.c_float]
         L.orc_exp.restype = C.c_float
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads.restype = None
+        L.orc_max_threads.restype = C.c_int
         L.orc_dec_create.argtypes = [C.c_int, C.c_int, C.c_int]
         L.orc_dec_create.restype = C.c_void_p
         L.orc_dec_set_layer.argtypes = [C.c_void_p, C.c_int] + [u16p] * 12 + [f32p] * 4
@@ -119,6 +122,15 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, nkeys: List[int
     out = np.empty((M, H, 64), dtype=np.uint16)
     lib().orc_attention(_p16(Q), _p16(K), _p16(V), nk.ctypes.data_as(i32p), M, H, T, _p16(out))
     return torch.from_numpy(out.view(np.float16).copy())
+
+
+def set_threads(n: int) -> None:
+    """OpenMP team size of the oracle's loops (results do not depend on it: every reduction is within one thread)."""
+    lib().orc_set_threads(int(n))
+
+
+def max_threads() -> int:
+    return int(lib().orc_max_threads())
 
 
 # ---------------------------------------------------------------- the decoder

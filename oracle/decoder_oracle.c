@@ -21,12 +21,17 @@
  * ("canonical order") that is emulated here with scalar loops over virtual
  * lanes; the CUDA kernels must reproduce it bit for bit.  Parity of this restatement with the
  * reference is UNPINNED by the reference (it ships no tests or golden vectors); it is pinned by
- * tests/test_oracle_vs_hf.py against transformers' own OPTDecoderLayer (fp32, eager attention).
+ * tests/test_oracle.py against fp32 logits of transformers' own OPTDecoderLayer stack + the reference's own
+ * embedding functions (tests/golden/decoder_hf_fp32.npz, decoder_hf_fp32_deep.npz: 24 layers x 320 positions)
+ * and, on the GPU box, by tests/test_gpu_hf.py (HF OPTDecoderLayer x 24 under fp16 autocast).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -385,6 +390,23 @@ static float *dup_f(const float *src, size_t n) {
   float *d = (float *)malloc(sizeof(float) * n);
   memcpy(d, src, sizeof(float) * n);
   return d;
+}
+
+/* OpenMP team size of every parallel loop below (bench.py picks the fastest for the host it runs on: on a box whose
+ * container sees more logical CPUs than it may use, the default of one thread per CPU is several times slower). */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : 1);
+#else
+  (void)n;
+#endif
+}
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
 }
 
 void *orc_dec_create(int n_layers, int vocab, int tmax) {

@@ -129,3 +129,30 @@ def test_oracle_generate_semantics():
     first = ids.index(eos)
     ids2, _ = o.generate(prefix, 16, eos_id=eos)
     assert ids2 == ids[:first + 1]
+
+
+def test_oracle_results_do_not_depend_on_the_openmp_team_size():
+    """bench.py picks the OpenMP team size that is fastest on the host (`orc_set_threads`); every reduction of the oracle
+    lives inside one thread, so ids and logits must be the same bits for any team size."""
+    from oracle import decoder as orc
+    from oracle.decoder import OracleDecoder
+    sd = decoder_sd(2)
+    prefix = random_prefix(1, seed=12)[0]
+    outs = []
+    try:
+        for t in (1, 3, max(1, orc.max_threads())):
+            orc.set_threads(t)
+            ids, logits = OracleDecoder(sd, 2, 257 + 12).generate(prefix, 12, keep_logits=True)
+            outs.append((ids, torch.as_tensor(np.asarray(logits)).clone()))
+    finally:
+        orc.set_threads(max(1, (os.cpu_count() or 1)))
+    for ids, lg in outs[1:]:
+        assert ids == outs[0][0]
+        assert torch.equal(lg.view(torch.int16) if lg.dtype == torch.float16 else lg, outs[0][1].view(torch.int16)
+                           if outs[0][1].dtype == torch.float16 else outs[0][1])
+
+
+def test_bench_usable_cpus():
+    import bench
+    n = bench._usable_cpus()
+    assert 1 <= n <= (os.cpu_count() or 1)
