@@ -71,7 +71,7 @@ __device__ __forceinline__ bool as_item(const AttnStreamArgs& a, int w, AsItem& 
   const int g = w % a.nseg, h = (w / a.nseg) % NHEAD;
   it.m = w / (a.nseg * NHEAD);
   it.h = h;
-  it.nk = a.nkeys[it.m];
+  it.nk = __ldcg(a.nkeys + it.m);   // from L2: the producer reads it before the grid dependency resolves, and both roles must see one value
   // never more keys than this launch has chunks for: a frozen cache slot (continuous batching) keeps an old, possibly
   // larger position than the bucket the launch was sized from; its output is discarded anyway
   it.n = min(it.nk, a.max_chunks * MA_ATTN_CHUNK);
