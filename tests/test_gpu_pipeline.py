@@ -418,3 +418,36 @@ def test_config1_mouse_example():
     _, prefix = model.point_encoder._last
     ref, _ = OracleDecoder(sd, 24, 257 + 9 * 64 + 2).generate(prefix[0].cpu(), 9 * 64 + 2)
     assert ids[0].tolist()[:len(ref)] == ref
+
+
+@gpu
+def test_config1_chain_against_reference_modules():
+    """BASELINE configs[0] on the GPU against tests/golden/config1_chain.npz (reference Dataset -> reference
+    AlignedShapeLatentPerceiver -> decoder oracle -> HF BertEncoder detokenizer, see make_golden_config1.py):
+      * decoder: greedy ids from the REFERENCE encoder's prefix are the committed ids, bit for bit (578 tokens);
+      * encoder: ma_encoder_forward on the mouse point cloud within the encoder tolerances of DESIGN.md section 6 of the
+        reference modules' output (fixture stored as fp16);
+      * detokenizer: ma_detokenize on the committed ids / point_feature gives the HF BertEncoder's bins (>= 97 %)."""
+    import os
+    import numpy as np
+    from meshanything_b200.decoder import DecoderArena, Generator
+    from meshanything_b200.encoder import EncoderArena, TokenizerArena
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    pc = torch.from_numpy(np.load(os.path.join(g, "config1_mouse.npz"))["pc_normal"][None])
+    fx = np.load(os.path.join(g, "config1_chain.npz"))
+    sd = ck.synthetic_state_dict(0)
+    n = 9 * 64 + 2
+    ref_prefix = torch.from_numpy(fx["prefix"]).float()
+    ids, lens = Generator(DecoderArena(sd, _dev()), 1, 257 + n).generate(ref_prefix[None].to(_dev()), n)
+    assert int(lens[0]) == n and ids[0].cpu().tolist() == fx["ids"].astype(np.int64).tolist()
+    pf, prefix = EncoderArena(sd, _dev()).forward(pc.to(_dev()))
+    ref_pf = torch.from_numpy(fx["point_feature"]).float()
+    e_pf, e_pre = (pf[0].cpu() - ref_pf).abs(), (prefix[0].cpu() - ref_prefix).abs()
+    print(f"config 1 encoder vs the reference modules: point_feature max {float(e_pf.max()):.4f} mean {float(e_pf.mean()):.5f}, "
+          f"prefix max {float(e_pre.max()):.4f} mean {float(e_pre.mean()):.5f}")
+    assert e_pf.max() < 1.5e-2 + 2e-3 and e_pf.mean() < 2.5e-3 and e_pre.max() < 4e-2 + 4e-3 and e_pre.mean() < 6e-3
+    coords = TokenizerArena(sd, _dev()).detokenize(torch.from_numpy(fx["ids"].astype(np.int32))[None].to(_dev()),
+                                                   ref_pf[None].to(_dev()), 64)
+    ref_coords = torch.from_numpy(fx["bins"].astype(np.float32)).view(64, 3, 3) / 128 - 0.5
+    assert not torch.isnan(coords).any()
+    assert float((coords[0].cpu() == ref_coords).float().mean()) >= 0.97

@@ -156,3 +156,36 @@ def test_bench_usable_cpus():
     import bench
     n = bench._usable_cpus()
     assert 1 <= n <= (os.cpu_count() or 1)
+
+
+def test_config1_chain_against_reference_modules():
+    """BASELINE configs[0] (the reference's CPU-runnable case) along the whole chain, on the CPU, against
+    tests/golden/config1_chain.npz (make_golden_config1.py): mouse.npy through the reference's own Dataset, the
+    reference's own AlignedShapeLatentPerceiver, the decoder oracle (578 greedy tokens), and transformers' BertEncoder
+    with meshanything.py's detokenizer code.
+      * oracle/torch_ref.py's encoder agrees with the reference's modules (fixture stored in fp16: tolerance
+        1e-3 * |x| + 1e-3);
+      * the C oracle reproduces the committed ids from the committed prefix exactly (pins it across toolchains,
+        OpenMP team sizes and refactors);
+      * torch_ref's detokenizer gives the HF BertEncoder's coordinate bins (>= 97 % equal, all faces present)."""
+    from meshanything_b200 import checkpoint as ck
+    from oracle import torch_ref
+    from oracle.decoder import OracleDecoder
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    pc = torch.from_numpy(np.load(os.path.join(g, "config1_mouse.npz"))["pc_normal"][None])
+    fx = np.load(os.path.join(g, "config1_chain.npz"))
+    sd = ck.synthetic_state_dict(0)
+    with torch.no_grad():
+        pf, prefix = torch_ref.encoder_forward(sd, pc)
+    for got, key in ((pf[0], "point_feature"), (prefix[0], "prefix")):
+        ref = torch.from_numpy(fx[key]).float()
+        assert ((got - ref).abs() <= 1e-3 * ref.abs() + 1e-3).all(), (key, float((got - ref).abs().max()))
+    n = 9 * 64 + 2
+    ids, _ = OracleDecoder(sd, 24, 257 + n).generate(torch.from_numpy(fx["prefix"]).float(), n)
+    assert ids == fx["ids"].astype(np.int64).tolist()
+    with torch.no_grad():
+        coords = torch_ref.detokenize(sd, torch_ref.postprocess_ids(torch.tensor([ids]), 64),
+                                      torch.from_numpy(fx["point_feature"]).float()[None])
+    ref_coords = torch.from_numpy(fx["bins"].astype(np.float32)).view(64, 3, 3) / 128 - 0.5
+    assert fx["face_mask"].all() and not torch.isnan(coords).any()
+    assert float((coords[0] == ref_coords).float().mean()) >= 0.97
