@@ -82,3 +82,31 @@ def test_default_build_uses_fhfma_and_the_fallback_variant_builds():
         for f in os.listdir(libdir):
             if "_nofhfma" in f:
                 os.remove(os.path.join(libdir, f))
+
+
+def _prototypes():
+    """{name: number of parameters} for every function the header declares (void parameter lists count 0)."""
+    src = open(os.path.join(ROOT, "include", "meshanything_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(r"\b(ma_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", src, flags=re.S):
+        params = m.group(2).strip()
+        out[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every entry point for which capi.py sets `argtypes` must take exactly as many arguments as the header's prototype:
+    a ctypes call with a stale signature corrupts the stack silently instead of failing."""
+    from meshanything_b200 import capi
+    lib = capi.lib()
+    protos = _prototypes()
+    assert set(_declared()) <= set(protos), sorted(set(_declared()) - set(protos))
+    checked = 0
+    for name, n in protos.items():
+        fn = getattr(lib, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, f"{name}: header has {n} parameters, capi.py declares {len(fn.argtypes)}"
+            checked += 1
+    assert checked >= 25, checked
